@@ -1,0 +1,196 @@
+// TEST INFRASTRUCTURE ONLY -- part of the CPU oracle (see oracle/README.md).
+//
+// The reference delegates acceleration-structure build and traversal to the Vulkan driver
+// (vkCmdBuildAccelerationStructuresKHR, reference ext/nvpro_core/nvvk/raytraceKHR_vk.cpp:216,375;
+// traceRayEXT, reference src/shaders/raytrace.projective.rgen:108,121).  What that black box
+// *returns* is mathematically defined: the nearest triangle hit of a two-level (instance ->
+// mesh) scene with rays transformed into object space and t preserved.  This file is a
+// deliberately plain CPU implementation of that definition: a binned-SAH BVH2 per mesh, one
+// over the instance boxes, a watertight ray/triangle test (Woop, Benthin, Wald 2013) and the
+// tie-break the driver leaves unspecified (lowest t, then lowest instance, then lowest
+// primitive -- SURVEY.md section 7 "hard parts" item 3).
+#pragma once
+#include <algorithm>
+#include <cfloat>
+#include <cstdint>
+#include <vector>
+
+#include "vecmath.h"
+
+namespace orc {
+
+struct Box {
+  vec3 lo{FLT_MAX, FLT_MAX, FLT_MAX}, hi{-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  void grow(vec3 p) {
+    lo = {std::fmin(lo.x, p.x), std::fmin(lo.y, p.y), std::fmin(lo.z, p.z)};
+    hi = {std::fmax(hi.x, p.x), std::fmax(hi.y, p.y), std::fmax(hi.z, p.z)};
+  }
+  void grow(const Box& b) {
+    grow(b.lo);
+    grow(b.hi);
+  }
+  float half_area() const {
+    vec3 e = hi - lo;
+    return e.x * e.y + e.y * e.z + e.z * e.x;
+  }
+  vec3 centre() const { return (lo + hi) * 0.5f; }
+};
+
+struct BvhNode {
+  Box box;
+  uint32_t left = 0;   // inner: index of left child (right = left + 1); leaf: first prim slot
+  uint32_t count = 0;  // 0 for inner nodes, else number of prims in the leaf
+};
+
+struct Bvh {
+  std::vector<BvhNode> nodes;
+  std::vector<uint32_t> prims;  // permutation of primitive ids
+
+  void build(const std::vector<Box>& boxes) {
+    const uint32_t n = (uint32_t)boxes.size();
+    prims.resize(n);
+    for (uint32_t i = 0; i < n; i++) prims[i] = i;
+    nodes.clear();
+    nodes.reserve(2 * n + 1);
+    nodes.emplace_back();
+    if (n == 0) return;
+    std::vector<vec3> cent(n);
+    for (uint32_t i = 0; i < n; i++) cent[i] = boxes[i].centre();
+    split(0, 0, n, boxes, cent);
+  }
+
+ private:
+  void split(uint32_t node, uint32_t first, uint32_t count, const std::vector<Box>& boxes,
+             const std::vector<vec3>& cent) {
+    Box nb, cb;
+    for (uint32_t i = first; i < first + count; i++) {
+      nb.grow(boxes[prims[i]]);
+      cb.grow(cent[prims[i]]);
+    }
+    nodes[node].box = nb;
+    if (count <= 2) {
+      nodes[node].left = first;
+      nodes[node].count = count;
+      return;
+    }
+    constexpr int NB = 16;
+    float best = FLT_MAX;
+    int best_axis = -1, best_bin = 0;
+    for (int a = 0; a < 3; a++) {
+      float lo = cb.lo[a], ext = cb.hi[a] - lo;
+      if (!(ext > 0.0f)) continue;
+      Box bb[NB];
+      uint32_t bc[NB] = {0};
+      float scale = NB / ext;
+      for (uint32_t i = first; i < first + count; i++) {
+        int b = std::min(NB - 1, (int)((cent[prims[i]][a] - lo) * scale));
+        bb[b].grow(boxes[prims[i]]);
+        bc[b]++;
+      }
+      float right_area[NB];
+      uint32_t right_cnt[NB];
+      Box acc;
+      uint32_t c = 0;
+      for (int b = NB - 1; b > 0; b--) {
+        if (bc[b]) acc.grow(bb[b]);
+        c += bc[b];
+        right_area[b] = c ? acc.half_area() : 0.0f;
+        right_cnt[b] = c;
+      }
+      acc = Box();
+      c = 0;
+      for (int b = 0; b < NB - 1; b++) {
+        if (bc[b]) acc.grow(bb[b]);
+        c += bc[b];
+        if (c == 0 || right_cnt[b + 1] == 0) continue;
+        float cost = acc.half_area() * c + right_area[b + 1] * right_cnt[b + 1];
+        if (cost < best) {
+          best = cost;
+          best_axis = a;
+          best_bin = b;
+        }
+      }
+    }
+    uint32_t mid;
+    if (best_axis < 0 || (count <= 4 && best >= nb.half_area() * count)) {
+      if (count <= 4) {
+        nodes[node].left = first;
+        nodes[node].count = count;
+        return;
+      }
+      // all centroids coincide: median split
+      mid = first + count / 2;
+    } else {
+      float lo = cb.lo[best_axis], scale = NB / (cb.hi[best_axis] - lo);
+      auto it = std::partition(prims.begin() + first, prims.begin() + first + count, [&](uint32_t p) {
+        int b = std::min(NB - 1, (int)((cent[p][best_axis] - lo) * scale));
+        return b <= best_bin;
+      });
+      mid = (uint32_t)(it - prims.begin());
+      if (mid == first || mid == first + count) mid = first + count / 2;
+    }
+    uint32_t l = (uint32_t)nodes.size();
+    nodes.emplace_back();
+    nodes.emplace_back();
+    nodes[node].left = l;
+    nodes[node].count = 0;
+    split(l, first, mid - first, boxes, cent);
+    split(l + 1, mid, first + count - mid, boxes, cent);
+  }
+};
+
+// Slab test against [tmin, tmax]; the far plane is widened by 2 ulp so the box test never
+// rejects a triangle the watertight triangle test would accept.
+inline bool hit_box(const Box& b, vec3 o, vec3 inv_d, float tmin, float tmax, float& tnear) {
+  float tx0 = (b.lo.x - o.x) * inv_d.x, tx1 = (b.hi.x - o.x) * inv_d.x;
+  float ty0 = (b.lo.y - o.y) * inv_d.y, ty1 = (b.hi.y - o.y) * inv_d.y;
+  float tz0 = (b.lo.z - o.z) * inv_d.z, tz1 = (b.hi.z - o.z) * inv_d.z;
+  float tn = std::fmax(std::fmax(std::fmin(tx0, tx1), std::fmin(ty0, ty1)), std::fmax(std::fmin(tz0, tz1), tmin));
+  float tf = std::fmin(std::fmin(std::fmax(tx0, tx1), std::fmax(ty0, ty1)), std::fmin(std::fmax(tz0, tz1), tmax));
+  tnear = tn;
+  return tn <= tf * 1.0000004f;
+}
+
+// Per-ray constants of the watertight test: dominant axis permutation and shear.
+struct RayShear {
+  int kx, ky, kz;
+  float Sx, Sy, Sz;
+  explicit RayShear(vec3 d) {
+    float ax = std::fabs(d.x), ay = std::fabs(d.y), az = std::fabs(d.z);
+    kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    kx = (kz + 1) % 3;
+    ky = (kx + 1) % 3;
+    if (d[kz] < 0.0f) std::swap(kx, ky);
+    Sx = d[kx] / d[kz];
+    Sy = d[ky] / d[kz];
+    Sz = 1.0f / d[kz];
+  }
+};
+
+// Watertight ray/triangle test.  No back-face culling (the reference sets
+// VK_GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE, src/pipeline/pipeline_raytrace.cpp:132).
+// Returns t and the Vulkan barycentrics (b1, b2): hit = (1-b1-b2) v0 + b1 v1 + b2 v2.
+inline bool hit_triangle(vec3 o, const RayShear& rs, vec3 v0, vec3 v1, vec3 v2, float& t, float& b1, float& b2) {
+  vec3 A = v0 - o, B = v1 - o, C = v2 - o;
+  float Ax = A[rs.kx] - rs.Sx * A[rs.kz], Ay = A[rs.ky] - rs.Sy * A[rs.kz];
+  float Bx = B[rs.kx] - rs.Sx * B[rs.kz], By = B[rs.ky] - rs.Sy * B[rs.kz];
+  float Cx = C[rs.kx] - rs.Sx * C[rs.kz], Cy = C[rs.ky] - rs.Sy * C[rs.kz];
+  float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {
+    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  float det = U + V + W;
+  if (det == 0.0f) return false;
+  float Az = rs.Sz * A[rs.kz], Bz = rs.Sz * B[rs.kz], Cz = rs.Sz * C[rs.kz];
+  float T = U * Az + V * Bz + W * Cz;
+  float inv = 1.0f / det;
+  t = T * inv;
+  b1 = V * inv;
+  b2 = W * inv;
+  return true;
+}
+
+}  // namespace orc
