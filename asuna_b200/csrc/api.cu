@@ -1,0 +1,797 @@
+// C ABI of libasuna_b200.so (include/asuna_b200.h): context, scene upload, acceleration-structure
+// build and the per-frame driver that sequences the wavefront kernels.
+//
+// This object sits where the reference's PipelineRaytrace sits (reference
+// src/pipeline/pipeline_raytrace.{h,cpp}): init() ≙ asuna_build_accel, run() ≙ asuna_render_frames,
+// the nine storage images of PipelineGraphics (reference src/pipeline/pipeline_graphics.cpp:126-138)
+// ≙ OutputImages.  There is no CPU fallback: without a CUDA device asuna_create fails.
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bvh_build.cuh"
+#include "integrator.cuh"
+
+using namespace asuna;
+
+namespace {
+struct HostMesh {
+  AsunaVertex* d_vertices = nullptr;
+  uint32_t* d_indices = nullptr;
+  uint32_t n_vertices = 0, n_tris = 0;
+  int node_base = 0, tri_base = 0;
+};
+struct HostTexture {
+  float4* d_texels = nullptr;
+  uint32_t w = 0, h = 0;
+};
+struct HostInstance {
+  float xform[16];
+  uint32_t mesh, material;
+  int32_t light;
+};
+struct TimedEvent {
+  cudaEvent_t a, b;
+  int kind;  // 0 trace, 1 shade/other
+};
+}  // namespace
+
+struct asuna_ctx {
+  int device = 0;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+
+  uint32_t W = 0, H = 0;
+  std::vector<HostTexture> textures;
+  HostTexture env[3];
+  std::vector<HostMesh> meshes;
+  std::vector<AsunaMaterial> materials;
+  std::vector<AsunaLight> lights;
+  std::vector<HostInstance> instances;
+  bool scene_dirty = true;
+
+  // device scene
+  BvhNode *d_blas_nodes = nullptr, *d_tlas_nodes = nullptr;
+  TriSlot* d_tris = nullptr;
+  uint32_t* d_tlas_leaf_inst = nullptr;
+  DInstance* d_instances = nullptr;
+  DMesh* d_meshes = nullptr;
+  AsunaMaterial* d_materials = nullptr;
+  AsunaLight* d_lights = nullptr;
+  DTexture* d_textures = nullptr;
+  float4 *d_mesh_lo = nullptr, *d_mesh_hi = nullptr;
+  SceneView view{};
+  BuildScratch scratch;
+  uint64_t accel_stats[4] = {0, 0, 0, 0};
+  bool may_pass_through = false;
+
+  // frame state
+  AsunaCamera cam{};
+  AsunaSunSky sunsky{};
+  AsunaState pc{};
+  uint32_t rank = 0, world = 1;
+  bool have_accum = false;
+  OutputImages out{};
+  float4* d_partial = nullptr;
+
+  // wavefront buffers
+  PathState ps{};
+  Counters* d_counters = nullptr;
+  Counters* h_counters = nullptr;  // pinned
+  uint32_t path_capacity = 0;
+  uint32_t max_batch_frames = 8;
+  LaunchDims dims;
+
+  // user-ray scratch
+  float4* d_user_rays = nullptr;
+  float* d_user_tuv = nullptr;
+  uint32_t* d_user_ip = nullptr;
+  uint8_t* d_user_occ = nullptr;
+  uint32_t user_capacity = 0;
+
+  AsunaStats stats{};
+  std::vector<TimedEvent> pending;
+  std::vector<cudaEvent_t> event_pool;
+};
+
+void asuna_set_cuda_error(asuna_ctx* ctx, cudaError_t e, const char* expr, const char* file, int line) {
+  char buf[512];
+  snprintf(buf, sizeof buf, "CUDA error %d (%s) at %s:%d in %s", (int)e, cudaGetErrorString(e), file, line, expr);
+  if (ctx) ctx->err = buf;
+}
+
+namespace {
+
+int fail(asuna_ctx* ctx, int code, const char* msg) {
+  ctx->err = msg;
+  return code;
+}
+
+template <class T>
+void free_dev(T*& p) {
+  if (p) cudaFree(p);
+  p = nullptr;
+}
+
+cudaEvent_t get_event(asuna_ctx* ctx) {
+  if (!ctx->event_pool.empty()) {
+    cudaEvent_t e = ctx->event_pool.back();
+    ctx->event_pool.pop_back();
+    return e;
+  }
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  return e;
+}
+struct ScopedTimer {  // brackets stream work with two events; elapsed time is collected at sync
+  asuna_ctx* ctx;
+  TimedEvent te;
+  ScopedTimer(asuna_ctx* c, int kind) : ctx(c) {
+    te.a = get_event(c);
+    te.b = get_event(c);
+    te.kind = kind;
+    cudaEventRecord(te.a, c->stream);
+  }
+  ~ScopedTimer() {
+    cudaEventRecord(te.b, ctx->stream);
+    ctx->pending.push_back(te);
+  }
+};
+void collect_timers(asuna_ctx* ctx) {
+  for (auto& te : ctx->pending) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, te.a, te.b) == cudaSuccess) {
+      if (te.kind == 0) ctx->stats.trace_ms += ms;
+      else if (te.kind == 1) ctx->stats.shade_ms += ms;
+      else if (te.kind == 2) ctx->stats.total_ms += ms;
+    }
+    ctx->event_pool.push_back(te.a);
+    ctx->event_pool.push_back(te.b);
+  }
+  ctx->pending.clear();
+}
+
+void free_scene_device(asuna_ctx* ctx) {
+  free_dev(ctx->d_blas_nodes);
+  free_dev(ctx->d_tlas_nodes);
+  free_dev(ctx->d_tris);
+  free_dev(ctx->d_tlas_leaf_inst);
+  free_dev(ctx->d_instances);
+  free_dev(ctx->d_meshes);
+  free_dev(ctx->d_materials);
+  free_dev(ctx->d_lights);
+  free_dev(ctx->d_textures);
+  free_dev(ctx->d_mesh_lo);
+  free_dev(ctx->d_mesh_hi);
+}
+
+void free_path_buffers(asuna_ctx* ctx) {
+  free_dev(ctx->ps.ray_o);
+  free_dev(ctx->ps.ray_d);
+  free_dev(ctx->ps.thr);
+  free_dev(ctx->ps.rad);
+  free_dev(ctx->ps.hit);
+  free_dev(ctx->ps.sh_o);
+  free_dev(ctx->ps.sh_d);
+  free_dev(ctx->ps.sh_l);
+  free_dev(ctx->ps.queue[0]);
+  free_dev(ctx->ps.queue[1]);
+  ctx->path_capacity = 0;
+}
+
+int ensure_path_buffers(asuna_ctx* ctx, uint32_t n_paths) {
+  if (n_paths <= ctx->path_capacity) return 0;
+  free_path_buffers(ctx);
+  size_t n = n_paths;
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.ray_o, n * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.ray_d, n * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.thr, n * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.rad, n * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.hit, n * sizeof(uint4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sh_o, n * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sh_d, n * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sh_l, n * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.queue[0], n * sizeof(uint32_t)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.queue[1], n * sizeof(uint32_t)));
+  ctx->path_capacity = n_paths;
+  return 0;
+}
+
+// world->object of a column-major 4x4 affine transform, inverted in double (what the driver
+// derives from VkAccelerationStructureInstanceKHR::transform)
+void make_instance_matrices(const float x[16], DInstance& d) {
+  float o2w[12];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 4; c++) o2w[r * 4 + c] = x[c * 4 + r];
+  double a[9], inv[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) a[r * 3 + c] = o2w[r * 4 + c];
+  double det = a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+  double id = 1.0 / det;
+  inv[0] = (a[4] * a[8] - a[5] * a[7]) * id, inv[1] = (a[2] * a[7] - a[1] * a[8]) * id, inv[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+  inv[3] = (a[5] * a[6] - a[3] * a[8]) * id, inv[4] = (a[0] * a[8] - a[2] * a[6]) * id, inv[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+  inv[6] = (a[3] * a[7] - a[4] * a[6]) * id, inv[7] = (a[1] * a[6] - a[0] * a[7]) * id, inv[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+  float w2o[12];
+  for (int r = 0; r < 3; r++) {
+    for (int c = 0; c < 3; c++) w2o[r * 4 + c] = (float)inv[r * 3 + c];
+    w2o[r * 4 + 3] = (float)-(inv[r * 3 + 0] * o2w[3] + inv[r * 3 + 1] * o2w[7] + inv[r * 3 + 2] * o2w[11]);
+  }
+  for (int r = 0; r < 3; r++) {
+    d.o2w[r] = make_float4(o2w[r * 4 + 0], o2w[r * 4 + 1], o2w[r * 4 + 2], o2w[r * 4 + 3]);
+    d.w2o[r] = make_float4(w2o[r * 4 + 0], w2o[r * 4 + 1], w2o[r * 4 + 2], w2o[r * 4 + 3]);
+  }
+}
+
+bool in_scope(uint32_t type) {
+  switch (type) {
+    case ASUNA_MAT_LAMBERTIAN:
+    case ASUNA_MAT_KANG18:
+    case ASUNA_MAT_EMISSIVE:
+    case ASUNA_MAT_PBR_METALNESS_ROUGHNESS:
+    case ASUNA_MAT_PLASTIC:
+    case ASUNA_MAT_ROUGH_PLASTIC:
+    case ASUNA_MAT_CONDUCTOR:
+    case ASUNA_MAT_DIELECTRIC: return true;
+    default: return false;
+  }
+}
+
+FrameParams make_frame_params(asuna_ctx* ctx) {
+  FrameParams fp{};
+  fp.cam = ctx->cam;
+  fp.sunsky = ctx->sunsky;
+  fp.pc = ctx->pc;
+  fp.width = ctx->W;
+  fp.height = ctx->H;
+  fp.n_pixels = ctx->W * ctx->H;
+  return fp;
+}
+
+int upload_user_rays(asuna_ctx* ctx, const float* rays, uint32_t n) {
+  if (n > ctx->user_capacity) {
+    free_dev(ctx->d_user_rays);
+    free_dev(ctx->d_user_tuv);
+    free_dev(ctx->d_user_ip);
+    free_dev(ctx->d_user_occ);
+    ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_user_rays, (size_t)n * 2 * sizeof(float4)));
+    ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_user_tuv, (size_t)n * 3 * sizeof(float)));
+    ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_user_ip, (size_t)n * 2 * sizeof(uint32_t)));
+    ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_user_occ, (size_t)n));
+    ctx->user_capacity = n;
+  }
+  if (rays)
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_user_rays, rays, (size_t)n * 8 * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+void asuna_abi_sizes(uint32_t out[6]) {
+  out[0] = sizeof(AsunaVertex), out[1] = sizeof(AsunaMaterial), out[2] = sizeof(AsunaLight);
+  out[3] = sizeof(AsunaCamera), out[4] = sizeof(AsunaState), out[5] = sizeof(AsunaSunSky);
+}
+
+int asuna_create(asuna_ctx** out, int gpu_id) {
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || gpu_id < 0 || gpu_id >= n) return ASUNA_E_NO_DEVICE;
+  if (cudaSetDevice(gpu_id) != cudaSuccess) return ASUNA_E_NO_DEVICE;
+  asuna_ctx* ctx = new asuna_ctx();
+  ctx->device = gpu_id;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, gpu_id) != cudaSuccess) {
+    delete ctx;
+    return ASUNA_E_NO_DEVICE;
+  }
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&ctx->d_counters, sizeof(Counters)) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_counters, sizeof(Counters)) != cudaSuccess ||
+      query_launch_dims(ctx->dims, ctx->sm_count) != cudaSuccess) {
+    delete ctx;
+    return ASUNA_E_CUDA;
+  }
+  ctx->pc.curFrame = -1;
+  ctx->pc.spp = 1;
+  ctx->pc.maxPathDepth = 3;
+  ctx->pc.envMapIntensity = 1.f;
+  const float id[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+  memcpy(ctx->cam.envTransform, id, sizeof id);
+  *out = ctx;
+  return 0;
+}
+
+void asuna_destroy(asuna_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  collect_timers(ctx);
+  for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  free_scene_device(ctx);
+  free_path_buffers(ctx);
+  for (auto& t : ctx->textures) free_dev(t.d_texels);
+  for (auto& t : ctx->env) free_dev(t.d_texels);
+  for (auto& m : ctx->meshes) {
+    free_dev(m.d_vertices);
+    free_dev(m.d_indices);
+  }
+  for (auto& p : ctx->out.img) free_dev(p);
+  free_dev(ctx->d_partial);
+  free_dev(ctx->d_counters);
+  free_dev(ctx->d_user_rays);
+  free_dev(ctx->d_user_tuv);
+  free_dev(ctx->d_user_ip);
+  free_dev(ctx->d_user_occ);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  ctx->scratch.release();
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* asuna_last_error(asuna_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int asuna_set_film(asuna_ctx* ctx, uint32_t w, uint32_t h) {
+  if (w == 0 || h == 0) return fail(ctx, ASUNA_E_INVALID, "film resolution must be non-zero");
+  cudaSetDevice(ctx->device);
+  ctx->W = w, ctx->H = h;
+  size_t bytes = (size_t)w * h * sizeof(float4);
+  for (auto& p : ctx->out.img) {
+    free_dev(p);
+    ASUNA_CUDA_CHECK(cudaMalloc(&p, bytes));
+    ASUNA_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, ctx->stream));
+  }
+  free_dev(ctx->d_partial);
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_partial, bytes));
+  ctx->have_accum = false;
+  return 0;
+}
+
+static int upload_texture(asuna_ctx* ctx, HostTexture& t, const float* rgba, uint32_t w, uint32_t h) {
+  free_dev(t.d_texels);
+  t.w = w, t.h = h;
+  ASUNA_CUDA_CHECK(cudaMalloc(&t.d_texels, (size_t)w * h * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMemcpy(t.d_texels, rgba, (size_t)w * h * sizeof(float4), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int asuna_add_texture(asuna_ctx* ctx, const float* rgba, uint32_t w, uint32_t h) {
+  if (!rgba || w == 0 || h == 0) return fail(ctx, ASUNA_E_INVALID, "empty texture");
+  cudaSetDevice(ctx->device);
+  ctx->textures.emplace_back();
+  int rc = upload_texture(ctx, ctx->textures.back(), rgba, w, h);
+  if (rc) {
+    ctx->textures.pop_back();
+    return rc;
+  }
+  ctx->scene_dirty = true;
+  return (int)ctx->textures.size() - 1;
+}
+
+int asuna_set_envmap(asuna_ctx* ctx, const float* rgba, const float* marginal, const float* conditional, uint32_t w,
+                     uint32_t h) {
+  if (!rgba || !marginal || !conditional || w == 0 || h == 0) return fail(ctx, ASUNA_E_INVALID, "empty env map");
+  cudaSetDevice(ctx->device);
+  const float* src[3] = {rgba, marginal, conditional};
+  for (int k = 0; k < 3; k++) {
+    int rc = upload_texture(ctx, ctx->env[k], src[k], w, h);
+    if (rc) return rc;
+  }
+  ctx->scene_dirty = true;
+  return 0;
+}
+
+int asuna_add_mesh(asuna_ctx* ctx, const AsunaVertex* v, uint32_t nv, const uint32_t* idx, uint32_t ni) {
+  if (!v || !idx || nv == 0 || ni < 3) return fail(ctx, ASUNA_E_INVALID, "empty mesh");
+  uint32_t nt = ni / 3;
+  for (uint32_t i = 0; i < nt * 3; i++)
+    if (idx[i] >= nv) return fail(ctx, ASUNA_E_INVALID, "index out of range");
+  cudaSetDevice(ctx->device);
+  HostMesh m;
+  m.n_vertices = nv, m.n_tris = nt;
+  ASUNA_CUDA_CHECK(cudaMalloc(&m.d_vertices, (size_t)nv * sizeof(AsunaVertex)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&m.d_indices, (size_t)nt * 3 * sizeof(uint32_t)));
+  ASUNA_CUDA_CHECK(cudaMemcpy(m.d_vertices, v, (size_t)nv * sizeof(AsunaVertex), cudaMemcpyHostToDevice));
+  ASUNA_CUDA_CHECK(cudaMemcpy(m.d_indices, idx, (size_t)nt * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  ctx->meshes.push_back(m);
+  ctx->scene_dirty = true;
+  return (int)ctx->meshes.size() - 1;
+}
+
+int asuna_add_material(asuna_ctx* ctx, const AsunaMaterial* m) {
+  if (!m) return fail(ctx, ASUNA_E_INVALID, "null material");
+  if (!in_scope(m->type)) return fail(ctx, ASUNA_E_UNSUPPORTED, "material type outside the hot-path scope (SURVEY.md 8f)");
+  ctx->materials.push_back(*m);
+  ctx->scene_dirty = true;
+  return (int)ctx->materials.size() - 1;
+}
+
+int asuna_set_lights(asuna_ctx* ctx, const AsunaLight* l, uint32_t n) {
+  if (!l || n == 0) return fail(ctx, ASUNA_E_INVALID, "light table must hold at least the dummy");
+  ctx->lights.assign(l, l + n);
+  ctx->scene_dirty = true;
+  return 0;
+}
+
+int asuna_add_instance(asuna_ctx* ctx, const float x[16], uint32_t mesh, uint32_t material, int32_t light) {
+  if (mesh >= ctx->meshes.size()) return fail(ctx, ASUNA_E_INVALID, "instance refers to unknown mesh");
+  if (light < 0 && material >= ctx->materials.size()) return fail(ctx, ASUNA_E_INVALID, "instance refers to unknown material");
+  HostInstance in;
+  memcpy(in.xform, x, sizeof in.xform);
+  in.mesh = mesh, in.material = material, in.light = light;
+  ctx->instances.push_back(in);
+  ctx->scene_dirty = true;
+  return (int)ctx->instances.size() - 1;
+}
+
+int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
+  cudaSetDevice(ctx->device);
+  if (ctx->instances.empty() || ctx->meshes.empty()) return fail(ctx, ASUNA_E_INVALID, "scene has no instances");
+  for (auto& in : ctx->instances)
+    if (in.light >= 0 && (size_t)in.light >= ctx->lights.size()) return fail(ctx, ASUNA_E_INVALID, "emitter instance refers to unknown light");
+  for (auto& m : ctx->materials) {
+    const int32_t ids[7] = {m.diffuseTextureId, m.roughnessTextureId, m.metalnessTextureId, m.radianceTextureId,
+                            m.normalTextureId,  m.tangentTextureId,   m.opacityTextureId};
+    for (int32_t id : ids)
+      if (id >= (int32_t)ctx->textures.size()) return fail(ctx, ASUNA_E_INVALID, "material refers to unknown texture");
+  }
+  cudaStreamSynchronize(ctx->stream);
+  free_scene_device(ctx);
+  cudaStream_t s = ctx->stream;
+
+  // layout of the node / triangle pools
+  size_t total_nodes = 0, total_tris = 0;
+  uint32_t max_prims = (uint32_t)ctx->instances.size();
+  for (auto& m : ctx->meshes) {
+    m.node_base = (int)total_nodes;
+    m.tri_base = (int)total_tris;
+    total_nodes += std::max<uint32_t>(m.n_tris - 1, 1);
+    total_tris += m.n_tris;
+    max_prims = std::max(max_prims, m.n_tris);
+  }
+  if (total_tris >= (1u << 27)) return fail(ctx, ASUNA_E_INVALID, "more than 2^27 triangles");
+  uint32_t n_inst = (uint32_t)ctx->instances.size(), n_mesh = (uint32_t)ctx->meshes.size();
+  ASUNA_CUDA_CHECK(ctx->scratch.reserve(max_prims));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_blas_nodes, total_nodes * sizeof(BvhNode)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tris, total_tris * sizeof(TriSlot)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_nodes, std::max<uint32_t>(n_inst - 1, 1) * sizeof(BvhNode)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_leaf_inst, n_inst * sizeof(uint32_t)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_instances, n_inst * sizeof(DInstance)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_meshes, n_mesh * sizeof(DMesh)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_mesh_lo, n_mesh * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_mesh_hi, n_mesh * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_materials, std::max<size_t>(ctx->materials.size(), 1) * sizeof(AsunaMaterial)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_lights, std::max<size_t>(ctx->lights.size(), 1) * sizeof(AsunaLight)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_textures, std::max<size_t>(ctx->textures.size(), 1) * sizeof(DTexture)));
+
+  // flat tables
+  std::vector<DInstance> hinst(n_inst);
+  for (uint32_t i = 0; i < n_inst; i++) {
+    const HostInstance& in = ctx->instances[i];
+    DInstance d{};
+    make_instance_matrices(in.xform, d);
+    d.blas_root = ctx->meshes[in.mesh].node_base;
+    d.mesh = in.mesh, d.material = in.material, d.light = in.light;
+    d.mat_type = in.light >= 0 ? 0xFFFFFFFFu : ctx->materials[in.material].type;
+    hinst[i] = d;
+  }
+  std::vector<DMesh> hmesh(n_mesh);
+  for (uint32_t i = 0; i < n_mesh; i++) hmesh[i] = DMesh{ctx->meshes[i].d_vertices, ctx->meshes[i].d_indices, ctx->meshes[i].n_tris, 0};
+  std::vector<DTexture> htex(ctx->textures.size());
+  for (size_t i = 0; i < htex.size(); i++) htex[i] = DTexture{ctx->textures[i].d_texels, (int)ctx->textures[i].w, (int)ctx->textures[i].h};
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_instances, hinst.data(), n_inst * sizeof(DInstance), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_meshes, hmesh.data(), n_mesh * sizeof(DMesh), cudaMemcpyHostToDevice, s));
+  if (!ctx->materials.empty())
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_materials, ctx->materials.data(), ctx->materials.size() * sizeof(AsunaMaterial), cudaMemcpyHostToDevice, s));
+  if (!ctx->lights.empty())
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_lights, ctx->lights.data(), ctx->lights.size() * sizeof(AsunaLight), cudaMemcpyHostToDevice, s));
+  if (!htex.empty())
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_textures, htex.data(), htex.size() * sizeof(DTexture), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors go out of scope below; also excludes H2D from build time
+
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0, s);
+  // bottom level: one BVH per mesh (≙ createBottomLevelAS)
+  for (uint32_t i = 0; i < n_mesh; i++) {
+    HostMesh& m = ctx->meshes[i];
+    launch_tri_boxes(s, m.d_vertices, m.d_indices, m.n_tris, ctx->scratch);
+    launch_lbvh(s, m.n_tris, ctx->d_blas_nodes, m.node_base, m.tri_base, ctx->scratch, ctx->d_mesh_lo + i, ctx->d_mesh_hi + i);
+    launch_emit_tris(s, m.d_vertices, m.d_indices, m.n_tris, ctx->scratch.vals[0], ctx->d_tris + m.tri_base);
+  }
+  // top level over the instance boxes (≙ createTopLevelAS)
+  launch_instance_boxes(s, ctx->d_instances, ctx->d_mesh_lo, ctx->d_mesh_hi, n_inst, ctx->scratch);
+  launch_lbvh(s, n_inst, ctx->d_tlas_nodes, 0, 0, ctx->scratch, nullptr, nullptr);
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tlas_leaf_inst, ctx->scratch.vals[0], n_inst * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  cudaEventRecord(e1, s);
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
+  ASUNA_CUDA_CHECK(cudaGetLastError());
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  ctx->stats.build_ms = ms;
+  if (out_ms) *out_ms = ms;
+
+  // SAH cost of the emitted BLASes (for asuna_accel_stats); normalised by each root's half area on the host side
+  {
+    double* d_cost = nullptr;
+    ASUNA_CUDA_CHECK(cudaMalloc(&d_cost, sizeof(double)));
+    ASUNA_CUDA_CHECK(cudaMemsetAsync(d_cost, 0, sizeof(double), s));
+    launch_sah_cost(s, ctx->d_blas_nodes, 0, (int)total_nodes, d_cost);
+    double cost = 0.0;
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(&cost, d_cost, sizeof(double), cudaMemcpyDeviceToHost, s));
+    ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
+    cudaFree(d_cost);
+    ctx->accel_stats[0] = total_nodes;
+    ctx->accel_stats[1] = total_tris;
+    ctx->accel_stats[2] = 0;
+    ctx->accel_stats[3] = (uint64_t)(cost * 1000.0);
+  }
+
+  ctx->view.tlas_nodes = ctx->d_tlas_nodes;
+  ctx->view.tlas_leaf_inst = ctx->d_tlas_leaf_inst;
+  ctx->view.blas_nodes = ctx->d_blas_nodes;
+  ctx->view.tris = ctx->d_tris;
+  ctx->view.instances = ctx->d_instances;
+  ctx->view.meshes = ctx->d_meshes;
+  ctx->view.materials = ctx->d_materials;
+  ctx->view.lights = ctx->d_lights;
+  ctx->view.textures = ctx->d_textures;
+  for (int k = 0; k < 3; k++) ctx->view.env[k] = DTexture{ctx->env[k].d_texels, (int)ctx->env[k].w, (int)ctx->env[k].h};
+  ctx->view.n_instances = n_inst;
+  ctx->may_pass_through = false;
+  for (auto& m : ctx->materials)
+    if ((m.type == ASUNA_MAT_PBR_METALNESS_ROUGHNESS && (m.opacityTextureId >= 0 || m.specular > 0.f)) ||
+        (m.type == ASUNA_MAT_KANG18 && (m.opacityTextureId >= 0 || m.metalness > 0.f)))
+      ctx->may_pass_through = true;
+  ctx->scene_dirty = false;
+  return 0;
+}
+
+int asuna_set_camera(asuna_ctx* ctx, const AsunaCamera* c) {
+  if (!c) return fail(ctx, ASUNA_E_INVALID, "null camera");
+  if (c->type != ASUNA_CAMERA_PERSPECTIVE && c->type != ASUNA_CAMERA_OPENCV) return fail(ctx, ASUNA_E_INVALID, "unknown camera type");
+  ctx->cam = *c;
+  return 0;
+}
+int asuna_set_sunsky(asuna_ctx* ctx, const AsunaSunSky* s) {
+  if (!s) return fail(ctx, ASUNA_E_INVALID, "null sunsky");
+  ctx->sunsky = *s;
+  return 0;
+}
+int asuna_set_state(asuna_ctx* ctx, const AsunaState* st) {
+  if (!st) return fail(ctx, ASUNA_E_INVALID, "null state");
+  if (st->spp != 1) return fail(ctx, ASUNA_E_INVALID, "spp must be 1 per frame (reference tracer.cpp:211)");
+  if (st->nMultiChannel > ASUNA_NUM_OUTPUT_IMAGES - 1) return fail(ctx, ASUNA_E_INVALID, "more than 8 output channels");
+  if (st->numLights < 0 || (size_t)st->numLights + 1 > std::max<size_t>(ctx->lights.size(), 1))
+    return fail(ctx, ASUNA_E_INVALID, "numLights exceeds the uploaded light table");
+  if (st->hasEnvMap == 1 && !ctx->env[0].d_texels) return fail(ctx, ASUNA_E_INVALID, "hasEnvMap set but no env map uploaded");
+  ctx->pc = *st;
+  return 0;
+}
+int asuna_reset_frame(asuna_ctx* ctx) {
+  ctx->pc.curFrame = -1;
+  ctx->have_accum = false;
+  return 0;
+}
+int asuna_set_partition(asuna_ctx* ctx, uint32_t rank, uint32_t world) {
+  if (world == 0 || rank >= world) return fail(ctx, ASUNA_E_INVALID, "bad partition");
+  ctx->rank = rank, ctx->world = world;
+  return 0;
+}
+
+static int render_batch(asuna_ctx* ctx, const int* frames, uint32_t n_frames) {
+  cudaStream_t s = ctx->stream;
+  FrameParams fp = make_frame_params(ctx);
+  fp.n_frames = n_frames;
+  for (uint32_t i = 0; i < n_frames; i++) fp.frame_ids[i] = frames[i];
+  fp.first_is_replace = ctx->have_accum ? 0u : 1u;
+  uint32_t n_paths = fp.n_pixels * n_frames;
+  int rc = ensure_path_buffers(ctx, n_paths);
+  if (rc) return rc;
+  ScopedTimer total(ctx, 2);
+  ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), s));
+  {
+    ScopedTimer t(ctx, 1);
+    launch_raygen(s, fp, ctx->ps, ctx->out, ctx->d_counters);
+  }
+  int iter = 0, qsel = 0;
+  auto bounce = [&]() {
+    {
+      ScopedTimer t(ctx, 0);
+      launch_trace_closest(s, ctx->dims, ctx->view, ctx->ps, ctx->d_counters, iter, qsel);
+    }
+    {
+      ScopedTimer t(ctx, 1);
+      launch_shade(s, ctx->dims, ctx->view, fp, ctx->ps, ctx->out, ctx->d_counters, iter, qsel);
+    }
+    {
+      ScopedTimer t(ctx, 0);
+      launch_trace_shadow(s, ctx->dims, ctx->view, ctx->ps, ctx->d_counters, iter);
+    }
+    iter++;
+    qsel ^= 1;
+  };
+  int planned = std::min(std::max(ctx->pc.maxPathDepth, 0), ASUNA_MAX_ITERS);
+  for (int d = 0; d < planned; d++) bounce();
+  // opacity pass-through keeps the depth (brdf_pbr_metalness_roughness.rchit:156-160), so a path may
+  // need more iterations than maxPathDepth; only then is a host round trip needed.
+  while (ctx->may_pass_through && planned > 0 && iter < ASUNA_MAX_ITERS) {
+    uint32_t alive = 0;
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(&alive, &ctx->d_counters->queue[iter], sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (alive == 0) break;
+    bounce();
+  }
+  {
+    ScopedTimer t(ctx, 1);
+    launch_accumulate(s, fp, ctx->ps, ctx->out);
+  }
+  // ray statistics of this batch: summed on the host after the async copy lands (stream order)
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
+  for (int i = 0; i <= iter && i <= ASUNA_MAX_ITERS; i++) {
+    if (i < iter) ctx->stats.closest_rays += ctx->h_counters->queue[i];
+    if (i < iter) ctx->stats.shadow_rays += ctx->h_counters->shadow[i];
+    if (i < iter) ctx->stats.incoherent_closest_rays += ctx->h_counters->incoherent[i];
+  }
+  if (ctx->h_counters->stack_overflow) return fail(ctx, ASUNA_E_CUDA, "traversal stack overflow");
+  ctx->stats.paths += n_paths;
+  ctx->have_accum = true;
+  ASUNA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+
+int asuna_render_frames(asuna_ctx* ctx, uint32_t n) {
+  cudaSetDevice(ctx->device);
+  if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene changed since the last asuna_build_accel");
+  if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
+  std::vector<int> mine;
+  for (uint32_t f = 0; f < n; f++) {
+    ctx->pc.curFrame++;  // ≙ incrementFrame(), pipeline_raytrace.cpp:84-86
+    if ((uint32_t)ctx->pc.curFrame % ctx->world == ctx->rank) mine.push_back(ctx->pc.curFrame);
+  }
+  uint32_t batch = std::min<uint32_t>(ctx->max_batch_frames, ASUNA_MAX_BATCH_FRAMES);
+  // keep a batch under ~16 M paths
+  uint64_t px = (uint64_t)ctx->W * ctx->H;
+  while (batch > 1 && px * batch > (16ull << 20)) batch--;
+  for (size_t i = 0; i < mine.size(); i += batch) {
+    uint32_t nb = (uint32_t)std::min<size_t>(batch, mine.size() - i);
+    int rc = render_batch(ctx, mine.data() + i, nb);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+int asuna_sync(asuna_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
+  return 0;
+}
+
+int asuna_read_channel(asuna_ctx* ctx, int ch, float* out) {
+  if (ch < 0 || ch >= ASUNA_NUM_OUTPUT_IMAGES || !out) return fail(ctx, ASUNA_E_INVALID, "bad channel");
+  if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
+  cudaSetDevice(ctx->device);
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(out, ctx->out.img[ch], (size_t)ctx->W * ctx->H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int asuna_export_partial(asuna_ctx* ctx, void** out) {
+  if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
+  cudaSetDevice(ctx->device);
+  launch_export_partial(ctx->stream, ctx->out, ctx->d_partial, ctx->W * ctx->H, ctx->have_accum ? 1 : 0);
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  *out = ctx->d_partial;
+  return 0;
+}
+int asuna_import_partial(asuna_ctx* ctx) {
+  if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
+  cudaSetDevice(ctx->device);
+  launch_import_partial(ctx->stream, ctx->out, ctx->d_partial, ctx->W * ctx->H);
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ctx->have_accum = true;
+  return 0;
+}
+int asuna_channel_device_ptr(asuna_ctx* ctx, int ch, void** out) {
+  if (ch < 0 || ch >= ASUNA_NUM_OUTPUT_IMAGES || !out || ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "bad channel");
+  *out = ctx->out.img[ch];
+  return 0;
+}
+
+int asuna_get_stats(asuna_ctx* ctx, AsunaStats* out) {
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  collect_timers(ctx);
+  *out = ctx->stats;
+  return 0;
+}
+int asuna_reset_stats(asuna_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  collect_timers(ctx);
+  float b = ctx->stats.build_ms;
+  ctx->stats = AsunaStats{};
+  ctx->stats.build_ms = b;
+  return 0;
+}
+
+int asuna_trace_rays(asuna_ctx* ctx, const float* rays, uint32_t n, float* tuv, uint32_t* ip) {
+  if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  int rc = upload_user_rays(ctx, rays, n);
+  if (rc) return rc;
+  ASUNA_CUDA_CHECK(cudaMemsetAsync(&ctx->d_counters->stack_overflow, 0, sizeof(uint32_t), ctx->stream));
+  launch_trace_user(ctx->stream, ctx->view, ctx->d_user_rays, n, ctx->d_user_tuv, ctx->d_user_ip, nullptr, ctx->d_counters);
+  if (tuv) ASUNA_CUDA_CHECK(cudaMemcpyAsync(tuv, ctx->d_user_tuv, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ip, ctx->d_user_ip, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ASUNA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int asuna_occlusion_rays(asuna_ctx* ctx, const float* rays, uint32_t n, uint8_t* occ) {
+  if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  int rc = upload_user_rays(ctx, rays, n);
+  if (rc) return rc;
+  launch_trace_user(ctx->stream, ctx->view, ctx->d_user_rays, n, nullptr, nullptr, ctx->d_user_occ, ctx->d_counters);
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(occ, ctx->d_user_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ASUNA_CUDA_CHECK(cudaGetLastError());
+  return 0;
+}
+int asuna_trace_primary(asuna_ctx* ctx, uint32_t* ip, float* t) {
+  if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
+  if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
+  cudaSetDevice(ctx->device);
+  uint32_t n = ctx->W * ctx->H;
+  int rc = upload_user_rays(ctx, nullptr, n);
+  if (rc) return rc;
+  FrameParams fp = make_frame_params(ctx);
+  launch_primary_rays(ctx->stream, fp, ctx->d_user_rays);
+  launch_trace_user(ctx->stream, ctx->view, ctx->d_user_rays, n, ctx->d_user_tuv, ctx->d_user_ip, nullptr, ctx->d_counters);
+  std::vector<float> tuv((size_t)n * 3);
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(tuv.data(), ctx->d_user_tuv, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ip, ctx->d_user_ip, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ASUNA_CUDA_CHECK(cudaGetLastError());
+  for (uint32_t i = 0; i < n; i++) t[i] = tuv[3 * (size_t)i];
+  return 0;
+}
+int asuna_accel_stats(asuna_ctx* ctx, uint64_t out[4]) {
+  if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
+  memcpy(out, ctx->accel_stats, sizeof ctx->accel_stats);
+  return 0;
+}
+
+// Test hook (not part of the reference-facing surface): sorts n (key, value) pairs given as host
+// arrays with the builder's radix sort, so the sort can be checked bit-exactly on its own.
+int asuna_debug_radix_sort(asuna_ctx* ctx, uint64_t* keys, uint32_t* vals, uint32_t n) {
+  if (n == 0) return 0;
+  cudaSetDevice(ctx->device);
+  uint64_t* dk = nullptr;
+  uint32_t* dv = nullptr;
+  ASUNA_CUDA_CHECK(cudaMalloc(&dk, (size_t)n * sizeof(uint64_t)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&dv, (size_t)n * sizeof(uint32_t)));
+  ASUNA_CUDA_CHECK(cudaMemcpy(dk, keys, (size_t)n * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  ASUNA_CUDA_CHECK(cudaMemcpy(dv, vals, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  ASUNA_CUDA_CHECK(radix_sort_pairs(ctx->stream, dk, dv, n, ctx->scratch));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ASUNA_CUDA_CHECK(cudaMemcpy(keys, dk, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  ASUNA_CUDA_CHECK(cudaMemcpy(vals, dv, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  cudaFree(dk);
+  cudaFree(dv);
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,1010 @@
+// Device-side shading library of the wavefront integrator: RNG, samplers, texture / env-map
+// fetches, the sun & sky model, light sampling and the eight in-scope BSDFs.
+//
+// Semantics follow the reference GLSL (cited per function); the structure does not: there is no
+// ray payload and no shader binding table -- k_shade (integrator.cu) keeps the path in registers,
+// calls one of the `shade_*` functions below and scatters the results into the SoA path state.
+#pragma once
+#include "device_types.cuh"
+#include "vec.cuh"
+
+namespace asuna {
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kTwoPi = 6.28318530717958647692f;
+constexpr float kInvPi = 0.31830988618379067154f;
+constexpr float kInv2Pi = 0.15915494309189533577f;
+constexpr float kInv4Pi = 0.07957747154594766788f;
+constexpr float kPiOver2 = 1.57079632679489661923f;
+constexpr float kPiOver4 = 0.78539816339744830961f;
+constexpr float kEps = 0.001f;       // reference src/shaders/utils/math.glsl:13
+constexpr float kInfinity = 1e10f;   // math.glsl:14
+constexpr float kMinimum = 0.00001f; // math.glsl:15
+
+// BSDF / light flags, reference src/shaders/utils/structs.glsl:16-50
+enum : uint32_t {
+  kBsdfNull = 0,
+  kDiffuseReflection = 1u << 0,
+  kGlossyReflection = 1u << 2,
+  kSpecularReflection = 1u << 4,
+  kSpecularTransmission = 1u << 5,
+  kSmooth = (1u << 0) | (1u << 1) | (1u << 2) | (1u << 3),
+  kLightDelta = 1u << 0,
+  kLightArea = 1u << 1,
+};
+
+// ---- RNG: math.glsl:20-44 ------------------------------------------------------------------
+ADEV uint32_t xxhash32_seed(uint32_t px, uint32_t py, uint32_t pz) {
+  const uint32_t P0 = 2246822519U, P1 = 3266489917U, P2 = 668265263U, P3 = 374761393U;
+  uint32_t h = pz + P3 + px * P1;
+  h = P2 * __funnelshift_l(h, h, 17);
+  h += py * P1;
+  h = P2 * __funnelshift_l(h, h, 17);
+  h = P0 * (h ^ (h >> 15));
+  h = P1 * (h ^ (h >> 13));
+  return h ^ (h >> 16);
+}
+ADEV uint32_t pcg_next(uint32_t& state) {
+  uint32_t prev = state * 747796405u + 2891336453u;
+  uint32_t word = ((prev >> ((prev >> 28u) + 4u)) ^ prev) * 277803737u;
+  state = prev;
+  return (word >> 22u) ^ word;
+}
+// pcg * (1.0/float(0xffffffffu)): the divisor rounds to 2^32, result may be exactly 1.0f
+ADEV float rnd(uint32_t& seed) { return __uint2float_rn(pcg_next(seed)) * 2.3283064365386963e-10f; }
+ADEV float2 rnd2(uint32_t& seed) {
+  float a = rnd(seed);
+  float b = rnd(seed);
+  return make_float2(a, b);
+}
+
+// ---- small helpers: math.glsl:58-216 -------------------------------------------------------
+ADEV float3 make_normal(float3 n) {
+  float l = length(n);
+  return l == 0.0f ? n : n / l;
+}
+ADEV float safe_sqrt(float v) { return sqrtf(fmaxf(0.0f, v)); }
+ADEV float3 to_world(float3 X, float3 Y, float3 Z, float3 v) { return v.x * X + v.y * Y + v.z * Z; }
+ADEV float3 to_local(float3 X, float3 Y, float3 Z, float3 v) { return f3(dot(v, X), dot(v, Y), dot(v, Z)); }
+ADEV float3 uniform_sample_sphere(float2 u) {
+  float z = 1.0f - 2.0f * u.x;
+  float r = sqrtf(fmaxf(0.0f, 1.0f - z * z));
+  float phi = kTwoPi * u.y;
+  return f3(r * cosf(phi), r * sinf(phi), z);
+}
+ADEV float2 concentric_sample_disk(float2 u) {
+  float ox = 2.0f * u.x - 1.0f, oy = 2.0f * u.y - 1.0f;
+  if (ox == 0.0f && oy == 0.0f) return make_float2(0.0f, 0.0f);
+  float theta, r;
+  if (fabsf(ox) > fabsf(oy)) {
+    r = ox;
+    theta = kPiOver4 * (oy / ox);
+  } else {
+    r = oy;
+    theta = kPiOver2 - kPiOver4 * (ox / oy);
+  }
+  return make_float2(r * cosf(theta), r * sinf(theta));
+}
+ADEV float3 cosine_sample_hemisphere(float2 u) {
+  float2 d = concentric_sample_disk(u);
+  return f3(d.x, d.y, sqrtf(fmaxf(0.0f, 1.0f - d.x * d.x - d.y * d.y)));
+}
+ADEV float cosine_hemisphere_pdf(float c) { return c <= 0.0f ? 0.0f : c * kInvPi; }
+ADEV float power_heuristic(float a, float b) {
+  a = a * a;
+  b = b * b + a;
+  return b == 0.0f ? 0.0f : a / b;
+}
+ADEV void basis(float3 n, float3& f, float3& r) {
+  if (n.z < -0.999999f) {
+    f = f3(0, -1, 0);
+    r = f3(-1, 0, 0);
+  } else {
+    float a = 1.0f / (1.0f + n.z);
+    float b = -n.x * n.y * a;
+    f = f3(1.0f - n.x * n.x * a, b, -n.x);
+    r = f3(b, 1.0f - n.y * n.y * a, -n.y);
+  }
+}
+// math.glsl:241-266 (Waechter & Binder self-intersection offset)
+ADEV float offset_component(float p, float n) {
+  int of_i = (int)(256.0f * n);
+  float p_i = __int_as_float(__float_as_int(p) + ((p < 0) ? -of_i : of_i));
+  return fabsf(p) < (1.0f / 32.0f) ? p + (1.0f / 65536.0f) * n : p_i;
+}
+ADEV float3 offset_position_along_normal(float3 p, float3 n) {
+  return f3(offset_component(p.x, n.x), offset_component(p.y, n.y), offset_component(p.z, n.z));
+}
+ADEV float luminance(float3 c) { return 0.2126f * c.x + 0.7152f * c.y + 0.0722f * c.z; }  // sun_and_sky.glsl:29-31
+
+// ---- textures: fp32 bilinear, REPEAT, LOD 0 (sampler of reference src/core/texture.cpp:99-107).
+// Texels are float4 in linear memory, so each of the four taps is one 128-bit load.
+ADEV int wrap_index(int i, int n) {
+  int m = i % n;
+  return m < 0 ? m + n : m;
+}
+ADEV float4 tex_bilinear(const DTexture& t, float u, float v) {
+  float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
+  if (!isfinite(x) || !isfinite(y)) return make_float4(0, 0, 0, 0);
+  float fx0 = floorf(x), fy0 = floorf(y);
+  float fx = x - fx0, fy = y - fy0;
+  int x0 = wrap_index((int)fmodf(fx0, (float)t.w), t.w), y0 = wrap_index((int)fmodf(fy0, (float)t.h), t.h);
+  int x1 = wrap_index(x0 + 1, t.w), y1 = wrap_index(y0 + 1, t.h);
+  float4 p00 = __ldg(&t.texels[(size_t)y0 * t.w + x0]), p10 = __ldg(&t.texels[(size_t)y0 * t.w + x1]);
+  float4 p01 = __ldg(&t.texels[(size_t)y1 * t.w + x0]), p11 = __ldg(&t.texels[(size_t)y1 * t.w + x1]);
+  float w00 = (1.0f - fx) * (1.0f - fy), w10 = fx * (1.0f - fy), w01 = (1.0f - fx) * fy, w11 = fx * fy;
+  return make_float4(w00 * p00.x + w10 * p10.x + w01 * p01.x + w11 * p11.x,
+                     w00 * p00.y + w10 * p10.y + w01 * p01.y + w11 * p11.y,
+                     w00 * p00.z + w10 * p10.z + w01 * p01.z + w11 * p11.z,
+                     w00 * p00.w + w10 * p10.w + w01 * p01.w + w11 * p11.w);
+}
+
+// ---- sun & sky: reference src/shaders/utils/sun_and_sky.glsl --------------------------------
+constexpr float kSsPi = 3.1415926535f;  // :24
+struct PerezCoeffs {
+  float A, B, C, D, E;
+};
+// one evaluator for the Perez form the reference spells out at :174-177, :185-188 and :220-223
+ADEV float perez_ratio(PerezCoeffs k, float cos_theta, float gamma, float cos_gamma, float theta_s, float cos_theta_s) {
+  float num = (1.0f + k.A * expf(k.B / cos_theta)) * (1.0f + k.C * expf(k.D * gamma) + k.E * cos_gamma * cos_gamma);
+  float den = (1.0f + k.A * expf(k.B / 1.0f)) * (1.0f + k.C * expf(k.D * theta_s) + k.E * cos_theta_s * cos_theta_s);
+  return num / den;
+}
+// :228-243 with :201-226 and :134-199 folded in
+ADEV float3 sky_env_color(float3 sun, float3 dir, float T) {
+  float theta_s = acosf(sun.z);
+  float chi = (4.0f / 9.0f - T / 120.0f) * (kSsPi - 2.0f * theta_s);
+  float lum = 1000.0f * ((4.0453f * T - 4.9710f) * tanf(chi) - 0.2155f * T + 2.4192f);
+  float cg_raw = dot(sun, dir);
+  {  // sky_luminance: cos_gamma clamped at 0 and mirrored above 1
+    float cg = cg_raw < 0.0f ? 0.0f : cg_raw;
+    if (cg > 1.0f) cg = 2.0f - cg;
+    PerezCoeffs kY = {0.178721f * T - 1.463037f, -0.355402f * T + 0.427494f, -0.022669f * T + 5.325056f,
+                      0.120647f * T - 2.577052f, -0.066967f * T + 0.370275f};
+    lum *= perez_ratio(kY, dir.z, acosf(cg), cg, theta_s, sun.z);
+  }
+  // sky_color_xyz: cos_gamma only mirrored
+  float cg = cg_raw > 1.0f ? 2.0f - cg_raw : cg_raw;
+  float gamma = acosf(cg);
+  float t2 = T * T, ts2 = theta_s * theta_s, ts3 = ts2 * theta_s;
+  float zx = ((+0.001650f * ts3 - 0.003742f * ts2 + 0.002088f * theta_s + 0) * t2 +
+              (-0.029028f * ts3 + 0.063773f * ts2 - 0.032020f * theta_s + 0.003948f) * T +
+              (+0.116936f * ts3 - 0.211960f * ts2 + 0.060523f * theta_s + 0.258852f));
+  float zy = ((+0.002759f * ts3 - 0.006105f * ts2 + 0.003162f * theta_s + 0) * t2 +
+              (-0.042149f * ts3 + 0.089701f * ts2 - 0.041536f * theta_s + 0.005158f) * T +
+              (+0.153467f * ts3 - 0.267568f * ts2 + 0.066698f * theta_s + 0.266881f));
+  PerezCoeffs kx = {-0.019257f * T - (0.29f - powf(sun.z, 0.5f) * 0.09f), -0.066513f * T + 0.000818f,
+                    -0.000417f * T + 0.212479f, -0.064097f * T - 0.898875f, -0.003251f * T + 0.045178f};
+  PerezCoeffs ky = {-0.016698f * T - 0.260787f, -0.094958f * T + 0.009213f, -0.007928f * T + 0.210230f,
+                    -0.044050f * T - 1.653694f, -0.010922f * T + 0.052919f};
+  float x = zx * perez_ratio(kx, dir.z, gamma, cg, theta_s, sun.z);
+  float y = zy * perez_ratio(ky, dir.z, gamma, cg, theta_s, sun.z);
+  float Y = lum, X = (x / y) * Y, Z = ((1.0f - x - y) / y) * Y;
+  return f3(3.241f * X - 1.537f * Y - 0.499f * Z, -0.969f * X + 1.876f * Y + 0.042f * Z,
+            0.056f * X - 0.204f * Y + 1.057f * Z) * kSsPi;
+}
+// :108-132
+ADEV float3 sun_disk_color(float3 sun, float T) {
+  if (!(sun.z > 0.0f)) return f3(0.0f);
+  const float3 ko = f3(12.0f, 8.5f, 0.9f), wl = f3(0.610f, 0.550f, 0.470f);
+  const float3 sol = f3(1.0f * 127500 / 0.9878f, 0.992f * 127500 / 0.9878f, 0.911f * 127500 / 0.9878f);
+  float m = 1.0f / (sun.z + 0.15f * powf(93.885f - acosf(sun.z) * 180 / kSsPi, -1.253f));
+  float beta = 0.04608f * T - 0.04586f;
+  float3 ta = exp3(-m * beta * pow3(wl, -1.3f));
+  float3 to = exp3(-m * ko * 0.0035f);
+  float3 tr = exp3(-m * 0.008735f * pow3(wl, -4.08f));
+  return tr * ta * to * sol;
+}
+// :33-106 specialised for the only caller (normal = +z): stencil direction for sample (sx, sy)
+ADEV float3 ground_stencil_dir(float sx, float sy) {
+  float lx = 2 * sx - 1, ly = 2 * sy - 1, r = 0.0f, phi = 0.0f;
+  if (!(lx == 0.0f && ly == 0.0f)) {
+    if (lx > -ly) {
+      if (lx > ly) { r = lx; phi = (kSsPi / 4.0f) * (1.0f + ly / lx); }
+      else { r = ly; phi = (kSsPi / 4.0f) * (3.0f - lx / ly); }
+    } else {
+      if (lx < ly) { r = -lx; phi = (kSsPi / 4.0f) * (5.0f + ly / lx); }
+      else { r = -ly; phi = (kSsPi / 4.0f) * (7.0f - lx / ly); }
+    }
+  }
+  float x = r * cosf(phi), y = r * sinf(phi);
+  float z2 = 1.0f - x * x - y * y;
+  float z = z2 > 0.0f ? sqrtf(z2) : 0.0f;
+  // xyz2dir with main = (0,0,1): u = (1,0,0), v = main x u = (0,1,0)
+  return f3(x, y, z);
+}
+ADEV float3 tweak_vector(float3 d, int y_is_up, float horiz_height) {  // :278-288
+  float3 o = (y_is_up == 1) ? f3(d.x, d.z, d.y) : d;
+  if (horiz_height != 0) {
+    o.z -= horiz_height;
+    o = normalize(o);
+  }
+  return o;
+}
+// :405-533
+__device__ __noinline__ float3 sun_and_sky(const AsunaSunSky& ss, float3 in_dir) {
+  float factor = 1.0f, night_factor = 1.0f;
+  float3 rgb_scale = f3(ss.rgb_unit_conversion);
+  float horiz = ss.horizon_height / 10.0f;
+  float3 dir = tweak_vector(in_dir, ss.y_is_up, horiz);
+  float haze = fmaxf(2.0f + ss.haze, 2.0f);
+  float sat;
+  {  // tweak_saturation :264-276
+    float s = ss.saturation;
+    if (s <= 1.0f) {
+      float h = clampf((haze - 2.0f) / 15.0f, 0.0f, 1.0f);
+      h = powf(h, 3.0f);
+      sat = (s * (1.0f - h)) + powf(s, 3.0f) * h;
+    } else
+      sat = 1.0f;
+  }
+  if (luminance(rgb_scale) < 0.0f) rgb_scale = f3(1.0f / 80000.0f);
+  rgb_scale *= ss.multiplier;
+  if (ss.multiplier <= 0.0f) return f3(0.0f);
+  float downness = dir.z;
+  float3 real_dir = dir;
+  if (dir.z < 0.001f) {
+    dir.z = 0.001f;
+    dir = normalize(dir);
+  }
+  float3 sun = tweak_vector(normalize(f3(ss.sun_direction)), ss.y_is_up, horiz);
+  float3 real_sun = sun;
+  if (sun.z < 0.001f) {
+    if (sun.z < 0.0f) {  // night_brightness_adjustment :396-403
+      const float lmt = 0.30901699437494742410229341718282f;
+      if (sun.z <= -lmt) factor = 0.0f;
+      else {
+        float f = (sun.z + lmt) / lmt;
+        f *= f;
+        factor = f * f;
+      }
+    }
+    sun.z = 0.001f;
+    sun = normalize(sun);
+  }
+  float3 tint = f3(0.0f);
+  if (factor > 0.0f) {
+    tint = sky_env_color(sun, dir, haze);
+    if (factor < 1.0f) tint *= factor;
+  }
+  float3 sun_color = sun_disk_color(sun, downness > 0 ? haze : 2.0f);
+  if (ss.sun_disk_intensity > 0.0f && ss.sun_disk_scale > 0.0f) {
+    float sun_angle = acosf(dot(real_dir, real_sun));
+    float sun_radius = 0.00465f * ss.sun_disk_scale * 10.0f;
+    if (sun_angle < sun_radius) {
+      float disk_scale = 1.0f, glow_scale = 1.0f;
+      if (ss.physically_scaled_sun == 1) {  // calc_physical_scale :312-394
+        float disk_r = 0.00465f * ss.sun_disk_scale, glow_r = disk_r * 10.0f;
+        float glow_integral = ss.sun_glow_intensity * ((4.f * kSsPi) - (24.f * kSsPi) / (glow_r * glow_r) +
+                                                        (24.f * kSsPi) * sinf(glow_r) / (glow_r * glow_r * glow_r));
+        float target = ss.sun_disk_intensity * kSsPi;
+        float max_glow = 0.5f * target;
+        if (glow_integral > max_glow) {
+          glow_scale *= max_glow / glow_integral;
+          target -= max_glow;
+        } else
+          target -= glow_integral;
+        float area = 2 * kSsPi * (1 - cosf(disk_r));
+        float target_intensity = target / area;
+        float actual_intensity = ss.sun_disk_intensity * 100.0f * (1.0f * area) / area;
+        disk_scale = (target_intensity == 0.0f) ? 0.0f : target_intensity / actual_intensity;
+      }
+      float f = (1.0f - sun_angle / sun_radius) * 10.0f;
+      f = powf(f / 10.0f, 3.0f) * 2.0f * ss.sun_glow_intensity * glow_scale +
+          smoothstepf(8.5f, 9.5f + (haze / 50.0f), f) * 100.0f * ss.sun_disk_intensity * disk_scale;
+      tint += sun_color * f;
+    }
+  }
+  float3 out = tint * rgb_scale;
+  if (downness <= 0.0f) {
+    float3 irrad = f3(0.0f);  // calc_irrad :245-262, float loop counters as written
+    for (float u = 1.f / 10.f; u < 1.f; u += 1.f / 5.f)
+      for (float v = 1.f / 10.f; v < 1.f; v += 1.f / 5.f) irrad += sky_env_color(sun, ground_stencil_dir(u, v), 2.0f);
+    irrad /= 25.0f;
+    float3 down = f3(ss.ground_color) * ((irrad + sun_color * sun.z) * rgb_scale);
+    if (factor < 1) down *= factor;
+    float blur = ss.horizon_blur / 10.0f;
+    if (blur > 0.0f) {
+      float d = fminf(-downness / blur, 1.0f);
+      d = smoothstepf(0.0f, 1.0f, d);
+      out = out * (1.0f - d) + down * d;
+      night_factor = 1.0f - d;
+    } else {
+      out = down;
+      night_factor = 0.0f;
+    }
+  }
+  // arch_colortweak :290-310
+  float inten = luminance(out);
+  float3 res = (sat <= 0.0f) ? f3(inten) : out * sat + f3(inten * (1.0f - sat));
+  res = res * f3(1.0f + ss.redblueshift, 1.0f, 1.0f - ss.redblueshift);
+  if (night_factor > 0.0f) {
+    float3 night = f3(ss.night_color) * night_factor;
+    res = f3(fmaxf(res.x, night.x), fmaxf(res.y, night.y), fmaxf(res.z, night.z));
+  }
+  return res * kSsPi;
+}
+
+// ---- environment map: reference src/shaders/utils/sample_light.glsl:84-129 ------------------
+struct EnvCtx {
+  const DTexture* env;  // [3]
+  const float* env_transform;
+  float res_x, res_y, intensity;
+};
+ADEV float2 env_dir_to_uv(float3 L, float& theta) {
+  theta = acosf(clampf(L.y, -1.0f, 1.0f));
+  return make_float2((kPi + atan2f(L.z, L.x)) * kInv2Pi, theta * kInvPi);
+}
+ADEV float env_pdf(const EnvCtx& e, float3 L) {
+  L = make_normal(mat4_vector_transposed(e.env_transform, L));
+  float theta;
+  float2 uv = env_dir_to_uv(L, theta);
+  float pdf = tex_bilinear(e.env[2], uv.x, uv.y).y * tex_bilinear(e.env[1], 0.f, uv.y).y;
+  float st = sinf(theta);
+  if (st == 0) return 0;
+  return (pdf * e.res_x * e.res_y) / (kTwoPi * kPi * st);
+}
+ADEV float3 env_eval(const EnvCtx& e, float3 L) {
+  L = make_normal(mat4_vector_transposed(e.env_transform, L));
+  float theta;
+  float2 uv = env_dir_to_uv(L, theta);
+  return e.intensity * f3(tex_bilinear(e.env[0], uv.x, uv.y));
+}
+ADEV float3 env_sample(const EnvCtx& e, float2 r, float3& L, float& pdf) {
+  float v = tex_bilinear(e.env[1], 0.f, r.x).x;  // marginal (fetched at u = 0: A.3-15)
+  float u = tex_bilinear(e.env[2], r.y, v).x;    // conditional
+  pdf = tex_bilinear(e.env[2], u, v).y * tex_bilinear(e.env[1], 0.f, v).y;
+  float phi = u * kTwoPi, theta = v * kPi;
+  float st = sinf(theta), ct = cosf(theta);
+  if (st == 0.0f) pdf = 0.0f;
+  pdf = (pdf * e.res_x * e.res_y) / (kTwoPi * kPi * st);
+  L = f3(-st * cosf(phi), ct, -st * sinf(phi));
+  L = make_normal(mat4_vector(e.env_transform, L));
+  return e.intensity * f3(tex_bilinear(e.env[0], u, v));
+}
+
+// ---- per-thread path / surface records -------------------------------------------------------
+struct Surface {  // HitState of rchit_layouts.glsl:37-58 minus the material copy
+  float2 uv;
+  float3 pos, V, N, geoN, ffN, X, Y;
+};
+struct LightSample {  // LightSamplingRecord, structs.glsl:52-63
+  float3 d, n;
+  float dist, pdf;
+  uint32_t flags;
+};
+struct PathRegs {
+  float3 ray_o, ray_d, throughput, radiance;
+  uint32_t seed;
+  int depth;
+  uint32_t bsdf_flags;
+  float bsdf_pdf;
+  bool stop;
+  // next-event estimation result (DirectLightRecord)
+  bool nee;
+  float3 nee_o, nee_d, nee_L;
+  float nee_dist;
+};
+struct ShadeEnv {  // read-only inputs of one shade call
+  const SceneView* scene;
+  const FrameParams* fp;
+  EnvCtx env;
+  float4* aov[ASUNA_NUM_OUTPUT_IMAGES - 1];  // channel cid -> image cid+1 (frame 0 only), else null
+};
+
+ADEV void configure_frame(const AsunaState& pc, Surface& s) {  // rchit_layouts.glsl:61-65
+  if (pc.useFaceNormal == 1) s.N = s.geoN;
+  basis(s.N, s.X, s.Y);
+  s.ffN = dot(s.N, s.V) > 0 ? s.N : -s.N;
+}
+
+// sample_light.glsl:10-82
+ADEV float3 sample_one_light(float2 r, const AsunaLight& light, float3 pos, LightSample& ls) {
+  float3 lu = f3(light.u), lv = f3(light.v), lp = f3(light.position);
+  if (light.type == ASUNA_LIGHT_RECT || light.type == ASUNA_LIGHT_TRIANGLE) {
+    float r1 = r.x;
+    float r2 = light.type == ASUNA_LIGHT_TRIANGLE ? (1 - r1) * r.y : r.y;  // A.3-2
+    ls.d = lp + lu * r1 + lv * r2 - pos;
+    ls.dist = length(ls.d);
+    float dist_sq = ls.dist * ls.dist;
+    ls.d /= ls.dist;
+    ls.n = make_normal(cross(lu, lv));
+    ls.pdf = dist_sq / (light.area * fabsf(dot(ls.n, ls.d)) + kEps);
+    ls.flags = kLightArea;
+    return f3(light.radiance);
+  } else if (light.type == ASUNA_LIGHT_DIRECTIONAL) {
+    ls.d = make_normal(f3(light.direction));
+    ls.n = -ls.d;
+    ls.dist = kInfinity;
+    ls.pdf = 1.0f;
+    ls.flags = kLightDelta;
+    return f3(light.radiance);
+  } else if (light.type == ASUNA_LIGHT_POINT) {
+    ls.d = lp - pos;
+    ls.n = -ls.d;
+    ls.dist = length(ls.d);
+    float dist_sq = ls.dist * ls.dist;
+    ls.d /= ls.dist + kEps;  // A.3-12
+    ls.pdf = 1.0f;
+    ls.flags = kLightDelta;
+    return f3(light.radiance) / (dist_sq + kEps);
+  }
+  return f3(0.0f);
+}
+
+// rchit_layouts.glsl:98-167.  Fills the NEE ray of `p` and returns the light radiance estimate.
+ADEV float3 sample_lights(const ShadeEnv& se, PathRegs& p, float3 pos, float3 normal, bool& visible, LightSample& ls) {
+  const AsunaState& pc = se.fp->pc;
+  const AsunaSunSky& sk = se.fp->sunsky;
+  bool allow_double = false;
+  float3 radiance = f3(0.0f);
+  ls.d = ls.n = f3(0.0f);
+  ls.dist = ls.pdf = 0.0f;
+  ls.flags = 0;  // A.3-7
+  bool has_env = (pc.hasEnvMap == 1 || sk.in_use == 1);
+  bool has_light = (pc.numLights > 0);
+  float env_sel = has_env ? (has_light ? 0.5f : 1.0f) : 0.0f;
+  float ana_sel = has_light ? (has_env ? 0.5f : 1.0f) : 0.0f;
+  float sel = rnd(p.seed);
+  if (sel < env_sel) {
+    ls.flags = kLightArea;
+    ls.dist = kInfinity;
+    ls.n = -make_normal(p.ray_d);
+    float2 u = rnd2(p.seed);
+    if (sk.in_use == 1) {
+      ls.d = uniform_sample_sphere(u);
+      ls.pdf = kInv4Pi;
+      radiance = sun_and_sky(sk, ls.d);
+    } else if (pc.hasEnvMap == 1) {
+      radiance = env_sample(se.env, u, ls.d, ls.pdf);
+    } else {
+      ls.d = uniform_sample_sphere(u);
+      ls.pdf = kInv4Pi;
+      radiance = f3(pc.bgColor);
+    }
+    radiance = radiance / env_sel;
+    allow_double = true;
+  } else if (sel < env_sel + ana_sel) {
+    int li = min(1 + (int)(rnd(p.seed) * pc.numLights), pc.numLights);
+    const AsunaLight light = se.scene->lights[li];
+    float2 r = rnd2(p.seed);
+    radiance = sample_one_light(r, light, pos, ls) * (float)pc.numLights / ana_sel;
+    allow_double = (light.doubleSide == 1);
+  }
+  p.nee_o = offset_position_along_normal(pos, normal);
+  p.nee_d = ls.d;
+  p.nee_dist = ls.dist;
+  visible = (dot(ls.d, normal) > 0.0f && ls.pdf > 0.0f);
+  visible = visible && (dot(ls.n, ls.d) < 0 || allow_double);
+  return radiance;
+}
+
+ADEV void store_direct(PathRegs& p, bool visible, float3 w, float bsdf_pdf, float3 radiance, const LightSample& ls) {
+  float3 Ld = f3(0.0f);
+  if (visible) Ld = power_heuristic(ls.pdf, bsdf_pdf) * w * radiance * p.throughput / (ls.pdf + kEps);
+  p.nee_L = Ld;
+  p.nee = visible;
+}
+// tail of every closest-hit main() that divides by (pdf + EPS)
+ADEV void next_ray(PathRegs& p, const Surface& s, float3 d, float pdf, uint32_t flags, float3 w, float3 offset_n) {
+  if (pdf <= 0.0f || length(w) == 0.0f) {
+    p.stop = true;
+    return;
+  }
+  p.bsdf_pdf = pdf;
+  p.bsdf_flags = flags;
+  p.ray_o = offset_position_along_normal(s.pos, offset_n);
+  p.ray_d = d;
+  p.throughput *= w / (pdf + kEps);
+}
+
+ADEV float4 tex(const ShadeEnv& se, int id, float2 uv) { return tex_bilinear(se.scene->textures[id], uv.x, uv.y); }
+ADEV void apply_normal_map(const ShadeEnv& se, const AsunaMaterial& m, Surface& s) {
+  if (m.normalTextureId >= 0) {
+    float3 n = 2.0f * f3(tex(se, m.normalTextureId, s.uv)) - 1.0f;
+    s.N = make_normal(to_world(s.X, s.Y, s.N, n));
+    configure_frame(se.fp->pc, s);
+  }
+}
+ADEV float3 diffuse_of(const ShadeEnv& se, const AsunaMaterial& m, const Surface& s) {
+  return m.diffuseTextureId >= 0 ? f3(tex(se, m.diffuseTextureId, s.uv)) : f3(m.diffuse);
+}
+ADEV void write_aov(const ShadeEnv& se, uint32_t pixel, int ch, float3 v) {
+  if (ch >= 0 && ch < ASUNA_NUM_OUTPUT_IMAGES - 1 && se.aov[ch]) se.aov[ch][pixel] = make_float4(v.x, v.y, v.z, 1.0f);
+}
+
+// ---- microfacet pieces shared by pbr / rough_plastic / kang18 (identical text in the three shaders)
+ADEV float sqr(float x) { return x * x; }
+ADEV float ggx_d(float HdotN, float HdotX, float HdotY, float ax, float ay) {
+  return 1 / (kPi * ax * ay * sqr(sqr(HdotX / ax) + sqr(HdotY / ay) + sqr(HdotN)) + kEps);
+}
+ADEV float3 ggx_sample(float2 u, float3 wo, float ax, float ay) {
+  float factor = safe_sqrt(u.x / fmaxf(1 - u.x, kEps));
+  float phi = kTwoPi * u.y;
+  float3 wh = make_normal(f3(-ax * factor * cosf(phi), -ay * factor * sinf(phi), 1.0f));
+  return reflect(-wo, wh);
+}
+ADEV float ggx_pdf(float3 wh, float3 wo, float ax, float ay) {
+  float HdotV = dot(wh, wo);
+  float3 wi = reflect(-wo, wh);
+  if (wi.z > 0.0f && wo.z > 0.0f && wh.z > 0.0f) return ggx_d(wh.z, wh.x, wh.y, ax, ay) * fabsf(wh.z) / (4 * HdotV + kEps);
+  return 0.0f;
+}
+ADEV float ggx_g1(float NdotV, float VdotX, float VdotY, float ax, float ay) {
+  if (NdotV <= 0.0f) return 0.0f;
+  return 1 / (NdotV + length(f3(ax * VdotX, ay * VdotY, NdotV)));
+}
+// brdf_plastic.rchit:12-41 == brdf_rough_plastic.rchit:12-41 (cosThetaT output unused by callers)
+ADEV float fresnel_dielectric_ext(float cos_i_, float eta) {
+  if (eta == 1) return 0.0f;
+  float scale = (cos_i_ > 0) ? 1 / eta : eta, cos_t2 = 1 - (1 - cos_i_ * cos_i_) * (scale * scale);
+  if (cos_t2 <= 0.0f) return 1.0f;
+  float ci = fabsf(cos_i_), ct = sqrtf(cos_t2);
+  float Rs = (ci - eta * ct) / (ci + eta * ct);
+  float Rp = (eta * ci - ct) / (eta * ci + ct);
+  return 0.5f * (Rs * Rs + Rp * Rp);
+}
+
+// ---- emitter hit: brdf_lambertian.rchit:44-68 -------------------------------------------------
+ADEV void shade_light_hit(const ShadeEnv& se, PathRegs& p, int light_id, float3 hit_pos) {
+  const AsunaLight light = se.scene->lights[light_id];
+  float3 dir = make_normal(p.ray_d);
+  float3 ln = make_normal(cross(f3(light.u), f3(light.v)));
+  float side = dot(ln, dir);
+  p.stop = true;
+  if (side > 0 && light.doubleSide == 0) return;
+  float mis = 1.0f;
+  if ((p.bsdf_flags & kSmooth) != 0 && p.depth != 1) {
+    float dist = length(hit_pos - p.ray_o);
+    float light_pdf = dist * dist / (light.area * fabsf(side) + kEps);
+    mis = power_heuristic(p.bsdf_pdf, light_pdf);
+  }
+  p.radiance += p.throughput * f3(light.radiance) * mis;
+}
+
+// ---- brdf_lambertian.rchit:70-151 -------------------------------------------------------------
+ADEV void shade_lambertian(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m, uint32_t pixel) {
+  const AsunaState& pc = se.fp->pc;
+  float3 kd = diffuse_of(se, m, s);
+  apply_normal_map(se, m, s);
+  if (p.depth == 1) {
+    write_aov(se, pixel, pc.diffuseOutChannel, kd);
+    write_aov(se, pixel, pc.normalOutChannel, s.N);
+    write_aov(se, pixel, pc.specularOutChannel, f3(0.0f));
+    write_aov(se, pixel, pc.tangentOutChannel, s.X);
+    write_aov(se, pixel, pc.roughnessOutChannel, f3(1, 1, 0));
+    write_aov(se, pixel, pc.positionOutChannel, s.pos);
+    write_aov(se, pixel, pc.uvOutChannel, f3(s.uv.x, s.uv.y, 1));
+  }
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float3 w = f3(0.0f);
+    float bpdf = 0.0f;
+    if (visible) {
+      float NdotL = dot(s.ffN, ls.d), NdotV = dot(s.ffN, s.V);
+      if (!(NdotL < 0 || NdotV < 0)) w = kd * kInvPi * NdotL;
+      if (ls.flags & kLightArea) bpdf = cosine_hemisphere_pdf(NdotL);
+    }
+    store_direct(p, visible, w, bpdf, radiance, ls);
+  }
+  float3 wi = cosine_sample_hemisphere(rnd2(p.seed));
+  float pdf = cosine_hemisphere_pdf(wi.z);
+  float3 w = kd * kInvPi * fabsf(wi.z);
+  if (pdf <= 0.0f || length(w) == 0.0f) {
+    p.stop = true;
+    return;
+  }
+  p.bsdf_pdf = pdf;
+  p.bsdf_flags = kDiffuseReflection;
+  p.ray_o = offset_position_along_normal(s.pos, s.ffN);
+  p.ray_d = to_world(s.X, s.Y, s.ffN, wi);
+  p.throughput *= w / pdf;  // lambertian divides by pdf, not pdf + EPS
+}
+
+// ---- brdf_emissive.rchit:12-26 ----------------------------------------------------------------
+ADEV void shade_emissive(const ShadeEnv& se, PathRegs& p, const Surface& s, const AsunaMaterial& m) {
+  p.stop = true;
+  float3 rad = f3(m.radiance);
+  if (m.radianceTextureId >= 0) rad = f3(m.radianceFactor) * f3(tex(se, m.radianceTextureId, s.uv));
+  if (se.fp->pc.ignoreEmissive == 0) p.radiance += rad * p.throughput;
+}
+
+// ---- bsdf_dielectric.rchit --------------------------------------------------------------------
+ADEV float dielectric_fresnel(float cos_i, float eta) {  // :12-24
+  float sin_t2 = eta * eta * (1.0f - cos_i * cos_i);
+  if (sin_t2 > 1.0f) return 1.0f;
+  float cos_t = sqrtf(fmaxf(1.0f - sin_t2, 0.0f));
+  float rs = (eta * cos_t - cos_i) / (eta * cos_t + cos_i);
+  float rp = (eta * cos_i - cos_t) / (eta * cos_i + cos_t);
+  return 0.5f * (rs * rs + rp * rp);
+}
+ADEV void shade_dielectric(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m) {  // :74-138
+  apply_normal_map(se, m, s);
+  float eta = dot(s.V, s.N) > 0.0f ? (1.0f / m.ior) : m.ior;
+  float F = dielectric_fresnel(fabsf(dot(s.V, s.ffN)), eta);
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float bpdf = 0.0f;  // eval(...,EArea) is identically 0 (A.3-4); pdf only matters for delta lights
+    if (visible && (ls.flags & kLightDelta)) {
+      if (dot(ls.d, s.ffN) > 0) {
+        if (fabsf(dot(reflect(-s.V, s.ffN), ls.d) - 1) < kEps) bpdf = F;
+      } else {
+        if (fabsf(dot(refract(-s.V, s.ffN, eta), ls.d) - 1) < kEps) bpdf = 1 - F;
+      }
+    }
+    store_direct(p, visible, f3(0.0f), bpdf, radiance, ls);
+  }
+  float u = rnd(p.seed);
+  float3 d, w;
+  float pdf;
+  uint32_t flags;
+  if (u < F) {
+    d = make_normal(reflect(-s.V, s.ffN));
+    pdf = F;
+    flags = kSpecularReflection;
+    w = f3(F);
+  } else {
+    d = make_normal(refract(-s.V, s.ffN, eta));
+    pdf = 1 - F;
+    flags = kSpecularTransmission;
+    w = f3((1 - F) * eta * eta);
+  }
+  next_ray(p, s, d, pdf, flags, w, signf(dot(d, s.N)) * s.N);
+}
+
+// ---- brdf_conductor.rchit ---------------------------------------------------------------------
+ADEV float conductor_reflectance(float eta, float k, float ci) {  // :14-32 (returns 0.5(Rs + Rs Rp), A.3-10)
+  float ci2 = ci * ci;
+  float si2 = fmaxf(1.0f - ci2, 0.0f);
+  float si4 = si2 * si2;
+  float inner = eta * eta - k * k - si2;
+  float a2b2 = sqrtf(fmaxf(inner * inner + 4.0f * eta * eta * k * k, 0.0f));
+  float a = sqrtf(fmaxf((a2b2 + inner) * 0.5f, 0.0f));
+  float Rs = ((a2b2 + ci2) - (2.0f * a * ci)) / ((a2b2 + ci2) + (2.0f * a * ci));
+  float Rp = ((ci2 * a2b2 + si4) - (2.0f * a * ci * si2)) / ((ci2 * a2b2 + si4) + (2.0f * a * ci * si2));
+  return 0.5f * (Rs + Rs * Rp);
+}
+ADEV void shade_conductor(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m) {  // :89-155
+  float3 kd = diffuse_of(se, m, s);
+  apply_normal_map(se, m, s);
+  float3 eta = f3(m.radiance), k = f3(m.radianceFactor);
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float bpdf = 0.0f;  // eval(...,EArea) = 0
+    if (visible) {
+      float NdotL = dot(ls.d, s.ffN), NdotV = dot(s.V, s.ffN);
+      if (!(NdotL < 0 || NdotV < 0 || (ls.flags & kLightDelta) == 0))
+        if (fabsf(dot(reflect(-s.V, s.ffN), ls.d) - 1) < kEps) bpdf = 1.0f;
+    }
+    store_direct(p, visible, f3(0.0f), bpdf, radiance, ls);
+  }
+  (void)rnd2(p.seed);  // sampleBsdf takes a vec2 it never uses (:68)
+  float NdotV = dot(s.V, s.ffN);
+  if (NdotV <= 0) {
+    p.stop = true;
+    return;
+  }
+  float3 d = reflect(-s.V, s.ffN);
+  float c = dot(s.ffN, d);
+  float3 w = kd * f3(conductor_reflectance(eta.x, k.x, c), conductor_reflectance(eta.y, k.y, c),
+                     conductor_reflectance(eta.z, k.z, c));
+  next_ray(p, s, d, 1.0f, kSpecularReflection, w, s.ffN);
+}
+
+// ---- brdf_plastic.rchit:133-204 ---------------------------------------------------------------
+ADEV void shade_plastic(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m) {
+  float3 kd = diffuse_of(se, m, s);
+  apply_normal_map(se, m, s);
+  float eta = m.ior, fdr = m.radiance[0];
+  float d_avg = luminance(kd), s_avg = luminance(f3(1.0f));
+  float spec_w = s_avg / (d_avg + s_avg);
+  float inv_eta2 = 1 / (eta * eta);
+  const float3 N = s.ffN, V = s.V;
+  float NdotV = dot(V, N);
+  float Fo = fresnel_dielectric_ext(NdotV, eta);
+  float prob_spec = (Fo * spec_w) / (Fo * spec_w + (1 - Fo) * (1 - spec_w));
+  float3 diff = kd;
+  diff /= (1.0f - diff * fdr);
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float3 w = f3(0.0f);
+    float bpdf = 0.0f;
+    if (visible) {
+      float NdotL = dot(ls.d, N);
+      if (!(NdotL < 0 || NdotV < 0)) {
+        float Fi = fresnel_dielectric_ext(NdotL, eta);
+        w = (1 - Fi) * (1 - Fo) * diff * inv_eta2 * kInvPi * NdotL;  // eval(:43-66) with EArea
+        if (ls.flags & kLightDelta) {                                // pdf(:68-92) with lRec.flags
+          if (fabsf(dot(reflect(-V, N), ls.d) - 1) < kEps) bpdf = prob_spec;
+        } else if (ls.flags & kLightArea)
+          bpdf = NdotL * (1 - prob_spec);
+      }
+    }
+    store_direct(p, visible, w, bpdf, radiance, ls);
+  }
+  float2 u = rnd2(p.seed);
+  if (NdotV <= 0) {
+    p.stop = true;
+    return;
+  }
+  if (u.x < prob_spec) {
+    next_ray(p, s, make_normal(reflect(-V, N)), prob_spec, kSpecularReflection, f3(Fo), s.ffN);
+  } else {
+    u.x = (u.x - prob_spec) / (1 + kEps - prob_spec);
+    float3 wi = cosine_sample_hemisphere(u);
+    float Fi = fresnel_dielectric_ext(wi.z, eta);
+    float pdf = (1 - prob_spec) * cosine_hemisphere_pdf(wi.z);
+    float3 w = (1 - Fi) * (1 - Fo) * inv_eta2 * diff * kInvPi * fabsf(wi.z);
+    next_ray(p, s, to_world(s.X, s.Y, N, wi), pdf, kDiffuseReflection, w, s.ffN);
+  }
+}
+
+// ---- brdf_rough_plastic.rchit -----------------------------------------------------------------
+struct RoughPlasticArgs {
+  float3 kd, ks;
+  float eta, fdr, inv_eta2, ax, ay;
+};
+ADEV float3 rough_plastic_eval(float3 L, const Surface& s, RoughPlasticArgs a) {  // :82-111 (flags = EArea)
+  const float3 N = s.ffN, V = s.V;
+  float NdotL = dot(L, N), NdotV = dot(V, N);
+  if (NdotL < 0 || NdotV < 0) return f3(0.0f);
+  float3 H = make_normal(L + V);
+  float Fs = fresnel_dielectric_ext(dot(H, V), a.eta);
+  float Gs = ggx_g1(NdotV, dot(V, s.X), dot(V, s.Y), a.ax, a.ay) * ggx_g1(NdotL, dot(L, s.X), dot(L, s.Y), a.ax, a.ay);
+  float Ds = ggx_d(dot(H, N), dot(H, s.X), dot(H, s.Y), a.ax, a.ay);
+  float3 w = a.ks * Fs * Gs * Ds * NdotL;
+  float Fo = fresnel_dielectric_ext(NdotV, a.eta), Fi = fresnel_dielectric_ext(NdotL, a.eta);
+  float3 diff = a.kd;
+  diff /= (1.0f - diff * a.fdr);
+  return w + (1 - Fi) * (1 - Fo) * diff * a.inv_eta2 * kInvPi * NdotL;
+}
+ADEV float rough_plastic_pdf(float3 L, const Surface& s, float ax, float ay, float eta, float substrate_w,
+                             uint32_t flags) {  // :113-136
+  const float3 N = s.ffN, V = s.V;
+  float NdotL = dot(L, N), NdotV = dot(V, N);
+  if (NdotL < 0 || NdotV < 0 || (flags & kLightArea) == 0) return 0.0f;
+  float Fo = fresnel_dielectric_ext(NdotV, eta);
+  float prob_spec = Fo / (Fo + substrate_w * (1.0f - Fo));
+  float3 wi = to_local(s.X, s.Y, N, L), wo = to_local(s.X, s.Y, N, V);
+  float3 wh = make_normal(wi + wo);
+  return prob_spec * ggx_pdf(wh, wo, ax, ay) + (1 - prob_spec) * cosine_hemisphere_pdf(wi.z);
+}
+ADEV void shade_rough_plastic(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m) {  // :191-269
+  RoughPlasticArgs a;
+  a.kd = diffuse_of(se, m, s);
+  float2 alpha = make_float2(m.anisoAlpha[0], m.anisoAlpha[1]);
+  if (m.roughnessTextureId >= 0) {
+    float4 c = tex(se, m.roughnessTextureId, s.uv);
+    alpha = make_float2(c.x, c.y);
+  }
+  apply_normal_map(se, m, s);
+  a.ks = f3(1.0f);
+  a.eta = m.ior;
+  a.fdr = m.radiance[0];
+  a.inv_eta2 = 1 / (a.eta * a.eta);
+  a.ax = fmaxf(kEps, alpha.x);
+  a.ay = fmaxf(kEps, alpha.y);
+  float substrate_w = luminance(a.kd);
+  const float3 N = s.ffN, V = s.V;
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float3 w = f3(0.0f);
+    float bpdf = 0.0f;
+    if (visible) {
+      // A.3-1: the NEE call sites (:234-240) pass the arguments in a different order than the
+      // signatures: eval receives (invEta2<-ax, ax<-ay, ay<-invEta2), pdf receives
+      // (ax<-eta, ay<-ax, eta<-ay).  Reproduced.
+      RoughPlasticArgs b = a;
+      b.inv_eta2 = a.ax;
+      b.ax = a.ay;
+      b.ay = a.inv_eta2;
+      w = rough_plastic_eval(ls.d, s, b);
+      bpdf = rough_plastic_pdf(ls.d, s, /*ax=*/a.eta, /*ay=*/a.ax, /*eta=*/a.ay, substrate_w, ls.flags);
+    }
+    store_direct(p, visible, w, bpdf, radiance, ls);
+  }
+  float2 u = rnd2(p.seed);
+  float NdotV = dot(V, N);
+  if (NdotV <= 0) {
+    p.stop = true;
+    return;
+  }
+  float Fo = fresnel_dielectric_ext(NdotV, a.eta);
+  float prob_spec = Fo / (Fo + substrate_w * (1.0f - Fo));
+  if (u.x < prob_spec) {
+    u.x = u.x / prob_spec;
+    float3 wo = to_local(s.X, s.Y, N, V);
+    float3 wi = ggx_sample(u, wo, a.ax, a.ay);
+    float3 L = to_world(s.X, s.Y, N, wi);
+    float3 H = make_normal(V + L);
+    float3 wh = make_normal(wi + wo);
+    float NdotL = dot(N, L);
+    float Fs = fresnel_dielectric_ext(dot(H, V), a.eta);
+    float Gs = ggx_g1(NdotV, dot(V, s.X), dot(V, s.Y), a.ax, a.ay) * ggx_g1(NdotL, dot(L, s.X), dot(L, s.Y), a.ax, a.ay);
+    float Ds = ggx_d(dot(H, N), dot(H, s.X), dot(H, s.Y), a.ax, a.ay);
+    next_ray(p, s, L, ggx_pdf(wh, wo, a.ax, a.ay) * prob_spec, kGlossyReflection, a.ks * Fs * Gs * Ds * NdotL, s.ffN);
+  } else {
+    u.x = (u.x - prob_spec) / (1 + kEps - prob_spec);
+    float3 wi = cosine_sample_hemisphere(u);
+    float Fi = fresnel_dielectric_ext(wi.z, a.eta);
+    float3 diff = a.kd;
+    diff /= (1.0f - diff * a.fdr);
+    float pdf = (1 - prob_spec) * cosine_hemisphere_pdf(wi.z);
+    float3 w = (1 - Fi) * (1 - Fo) * a.inv_eta2 * diff * kInvPi * fabsf(wi.z);
+    next_ray(p, s, to_world(s.X, s.Y, N, wi), pdf, kDiffuseReflection, w, s.ffN);
+  }
+}
+
+// ---- GGX + Lambert two-lobe BRDFs: pbr_metalness_roughness and kang18 ---------------------------
+// eval: pbr :57-86 (Schlick on mix(F0, albedo, metalness), diffuse scaled by 1-metalness),
+//       kang18 :61-90 (scalar Schlick times rhoSpec).  `spec_tint`/`f0` carry the difference.
+ADEV float3 two_lobe_eval(float3 L, const Surface& s, float3 diffuse_term, float3 f0, float3 spec_scale, float ax, float ay) {
+  const float3 N = s.ffN, V = s.V;
+  float NdotL = dot(N, L), NdotV = dot(N, V);
+  if (NdotL <= 0.0f || NdotV <= 0.0f) return f3(0.0f);
+  float3 H = make_normal(L + V);
+  float HdotV = dot(H, V);
+  float3 Fs = f0 + (1.0f - f0) * powf(clampf(1 - HdotV, 0, 1), 5.0f);
+  float Ds = ggx_d(dot(H, N), dot(H, s.X), dot(H, s.Y), ax, ay);
+  float Gs = ggx_g1(NdotV, dot(V, s.X), dot(V, s.Y), ax, ay) * ggx_g1(NdotL, dot(L, s.X), dot(L, s.Y), ax, ay);
+  return (diffuse_term + spec_scale * Fs * Ds * Gs) * NdotL;
+}
+ADEV float two_lobe_pdf(float3 L, const Surface& s, float ax, float ay, float p_diffuse, uint32_t flags) {  // pbr :88-105
+  if ((flags & kLightArea) == 0) return 0.0f;
+  const float3 N = s.ffN, V = s.V;
+  float NdotL = dot(N, L), NdotV = dot(N, V);
+  if (NdotL <= 0.0f || NdotV <= 0.0f) return 0.0f;
+  float3 H = make_normal(L + V);
+  float3 wh = make_normal(to_local(s.X, s.Y, N, H));
+  float3 wo = make_normal(to_local(s.X, s.Y, N, V));
+  float3 wi = make_normal(to_local(s.X, s.Y, N, L));
+  return p_diffuse * cosine_hemisphere_pdf(wi.z) + (1 - p_diffuse) * ggx_pdf(wh, wo, ax, ay);
+}
+// opacity pass-through, pbr :151-160 / kang18 :176-180: continue the same ray from behind the surface
+ADEV bool pass_through(PathRegs& p, const Surface& s, float opacity) {
+  if (rnd(p.seed) < opacity) {
+    p.ray_o = offset_position_along_normal(s.pos, -s.ffN);
+    p.depth--;
+    return true;
+  }
+  return false;
+}
+ADEV void two_lobe_sample(const ShadeEnv& se, PathRegs& p, const Surface& s, float3 diffuse_term, float3 f0,
+                          float3 spec_scale, float ax, float ay, float p_diffuse, bool times_cos) {
+  float2 u = rnd2(p.seed);  // argument evaluated before the lobe-select rand of the body (A.1)
+  const float3 N = s.ffN;
+  float3 wo = make_normal(to_local(s.X, s.Y, N, s.V));
+  float3 wi;
+  float pdf;
+  uint32_t flags;
+  if (rnd(p.seed) < p_diffuse) {
+    wi = cosine_sample_hemisphere(u);
+    flags = kDiffuseReflection;
+    pdf = cosine_hemisphere_pdf(wi.z);
+  } else {
+    wi = ggx_sample(u, wo, ax, ay);
+    pdf = ggx_pdf(make_normal(wi + wo), wo, ax, ay);
+    flags = kGlossyReflection;
+  }
+  float3 d = to_world(s.X, s.Y, N, wi);
+  float3 w = two_lobe_eval(d, s, diffuse_term, f0, spec_scale, ax, ay);
+  if (times_cos) w = w * fabsf(wi.z);  // pbr multiplies eval (which already holds NdotL) by |wi.z| again (:125-127)
+  next_ray(p, s, d, pdf, flags, w, s.ffN);
+}
+
+ADEV void shade_pbr(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m, uint32_t pixel) {  // :131-219
+  const AsunaState& pc = se.fp->pc;
+  float3 albedo = diffuse_of(se, m, s);
+  float metalness = m.metalnessTextureId >= 0 ? tex(se, m.metalnessTextureId, s.uv).x : m.metalness;
+  float roughness = m.roughnessTextureId >= 0 ? tex(se, m.roughnessTextureId, s.uv).x : m.roughness;
+  apply_normal_map(se, m, s);
+  float opacity = m.opacityTextureId >= 0 ? tex(se, m.opacityTextureId, s.uv).x : m.specular;
+  if (pass_through(p, s, opacity)) return;
+  float ax = fmaxf(sqr(roughness), 0.001f), ay = ax;
+  float eta = m.ior;
+  if (p.depth == 1) {
+    write_aov(se, pixel, pc.diffuseOutChannel, albedo);
+    write_aov(se, pixel, pc.normalOutChannel, s.ffN);
+  }
+  float F0 = sqr((eta - 1) / (eta + 1));
+  float3 f0 = mix3(f3(F0), albedo, metalness);
+  float3 diffuse_term = albedo * (1 - metalness) * kInvPi;
+  const float kDiffuseLobe = 0.2f;
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float3 w = f3(0.0f);
+    float bpdf = 0.0f;
+    if (visible) {
+      w = two_lobe_eval(ls.d, s, diffuse_term, f0, f3(1.0f), ax, ay);
+      bpdf = two_lobe_pdf(ls.d, s, ax, ay, kDiffuseLobe, ls.flags);
+    }
+    store_direct(p, visible, w, bpdf, radiance, ls);
+  }
+  two_lobe_sample(se, p, s, diffuse_term, f0, f3(1.0f), ax, ay, kDiffuseLobe, true);
+}
+
+ADEV void shade_kang18(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m, const DInstance& in,
+                       uint32_t pixel) {  // :141-249
+  const AsunaState& pc = se.fp->pc;
+  float3 kd = diffuse_of(se, m, s);
+  float3 ks = m.metalnessTextureId >= 0 ? f3(tex(se, m.metalnessTextureId, s.uv)) : f3(m.rhoSpec);
+  float2 alpha = make_float2(m.anisoAlpha[0], m.anisoAlpha[1]);
+  if (m.roughnessTextureId >= 0) {
+    float4 c = tex(se, m.roughnessTextureId, s.uv);
+    alpha = make_float2(c.x, c.y);
+  }
+  float opacity = m.opacityTextureId >= 0 ? tex(se, m.opacityTextureId, s.uv).x : m.metalness;
+  if (m.normalTextureId >= 0) {  // object-space normal map (:157-163)
+    float3 n = 2.0f * f3(tex(se, m.normalTextureId, s.uv)) - 1.0f;
+    s.N = make_normal(xf_normal(in.w2o, n));
+    configure_frame(pc, s);
+  }
+  if (m.tangentTextureId >= 0) {  // (:165-169)
+    float3 t = 2.0f * f3(tex(se, m.tangentTextureId, s.uv)) - 1.0f;
+    s.X = make_normal(xf_normal(in.w2o, t));
+  }
+  s.Y = make_normal(cross(s.N, s.X));
+  s.X = make_normal(cross(s.Y, s.N));
+  s.ffN = dot(s.N, s.V) > 0 ? s.N : -s.N;
+  if (pass_through(p, s, opacity)) return;
+  float ax = fmaxf(alpha.x, kEps), ay = fmaxf(alpha.y, kEps);
+  float eta = m.ior;
+  if (p.depth == 1) {
+    write_aov(se, pixel, pc.diffuseOutChannel, kd);
+    write_aov(se, pixel, pc.normalOutChannel, s.ffN);
+    write_aov(se, pixel, pc.specularOutChannel, ks);
+    write_aov(se, pixel, pc.tangentOutChannel, s.X);
+    write_aov(se, pixel, pc.roughnessOutChannel, f3(ax, ay, 0));
+    write_aov(se, pixel, pc.positionOutChannel, s.pos);
+    write_aov(se, pixel, pc.uvOutChannel, f3(s.uv.x, s.uv.y, 1));
+  }
+  float F0 = sqr((eta - 1) / (eta + 1));
+  auto lum709 = [](float3 c) { return 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z; };  // :57-59
+  float pd = lum709(kd), ps = lum709(ks);
+  float p_diffuse = pd / (pd + ps + kEps);
+  float3 diffuse_term = kd * kInvPi;
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float3 w = f3(0.0f);
+    float bpdf = 0.0f;
+    if (visible) {
+      w = two_lobe_eval(ls.d, s, diffuse_term, f3(F0), ks, ax, ay);
+      bpdf = two_lobe_pdf(ls.d, s, ax, ay, p_diffuse, ls.flags);
+    }
+    store_direct(p, visible, w, bpdf, radiance, ls);
+  }
+  two_lobe_sample(se, p, s, diffuse_term, f3(F0), ks, ax, ay, p_diffuse, false);
+}
+
+// ---- miss: raytrace.default.rmiss:24-55 -------------------------------------------------------
+ADEV void shade_miss(const ShadeEnv& se, PathRegs& p) {
+  const AsunaState& pc = se.fp->pc;
+  const AsunaSunSky& sk = se.fp->sunsky;
+  p.stop = true;
+  float3 d = p.ray_d, env;
+  if (sk.in_use == 1) env = sun_and_sky(sk, d);
+  else if (pc.hasEnvMap == 1) env = env_eval(se.env, d);
+  else env = f3(pc.bgColor);
+  float mis = 1.0f;
+  if (p.depth != 1 && (p.bsdf_flags & kSmooth) != 0) {
+    float env_pdf_v = (sk.in_use != 1 && pc.hasEnvMap == 1) ? env_pdf(se.env, d) : kInv4Pi;
+    mis = power_heuristic(p.bsdf_pdf, env_pdf_v);
+  }
+  p.radiance += p.throughput * env * mis;
+}
+
+}  // namespace asuna
