@@ -80,7 +80,11 @@ ADEV bool hit_triangle(const RaySpace& r, float3 v0, float3 v1, float3 v2, float
   float Ax = comp(A, r.kx) - r.Sx * Akz, Ay = comp(A, r.ky) - r.Sy * Akz;
   float Bx = comp(B, r.kx) - r.Sx * Bkz, By = comp(B, r.ky) - r.Sy * Bkz;
   float Cx = comp(C, r.kx) - r.Sx * Ckz, Cy = comp(C, r.ky) - r.Sy * Ckz;
-  float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
+  // Edge functions with individually rounded products (no FMA contraction): the neighbour across a
+  // shared edge then computes the exact negative, which is what makes the test watertight.
+  float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+  float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+  float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
   if (U == 0.0f || V == 0.0f || W == 0.0f) {  // edge case: redo the edge functions in double
     U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
     V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);

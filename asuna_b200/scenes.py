@@ -253,8 +253,9 @@ def cornell_materials(width=256, height=256, spp=16, depth=5, env=False, lights=
                                diffuseTextureId=t("albedo"), roughnessTextureId=t("rough"),
                                metalnessTextureId=t("metal"), normalTextureId=t("normal"),
                                opacityTextureId=t("opacity")))
-    sc.add_material("kang", mat(S.MAT_KANG18, diffuse=(.3, .4, .6), rhoSpec=(.5, .5, .4), anisoAlpha=(.2, .08),
-                                metalness=0.0, diffuseTextureId=t("albedo")))
+    # kang18 takes the diffuse texture *or* the constant (reference src/loader/material.cpp:166-169)
+    sc.add_material("kang", mat(S.MAT_KANG18, diffuse=(0, 0, 0) if textured else (.3, .4, .6), rhoSpec=(.5, .5, .4),
+                                anisoAlpha=(.2, .08), metalness=0.0, diffuseTextureId=t("albedo")))
     sc.add_material("glow", mat(S.MAT_EMISSIVE, radiance=(2.0, 1.5, 3.0)))
     if lights in ("rect", "all"):
         sc.add_light(rect_light((0.35, 0.999, 0.35), (0.65, 0.999, 0.35), (0.35, 0.999, 0.65), (17, 12, 4)))

@@ -1,0 +1,120 @@
+"""Per-kernel differential tests: radix sort bit-exact, traversal against the
+oracle on random rays, any-hit occlusion, watertightness on shared edges / vertices, BVH build stats."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from asuna_b200 import host, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def _sort(ctx, keys, vals):
+    k = np.ascontiguousarray(keys, np.uint64).copy()
+    v = np.ascontiguousarray(vals, np.uint32).copy()
+    f = ctx.L.lib.asuna_debug_radix_sort
+    f.restype = C.c_int
+    rc = f(ctx.h, k.ctypes.data_as(C.c_void_p), v.ctypes.data_as(C.c_void_p), C.c_uint32(k.size))
+    assert rc == 0
+    return k, v
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 32, 33, 4095, 4096, 4097, 100003, 1 << 20])
+def test_radix_sort_is_exact_and_stable(gpu_ctx, n):
+    rng = np.random.RandomState(n)
+    keys = rng.randint(0, 1 << 62, size=n, dtype=np.int64).astype(np.uint64)
+    keys[rng.rand(n) < 0.3] &= np.uint64(0xFF)  # many duplicates: stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    k, v = _sort(gpu_ctx, keys, vals)
+    order = np.argsort(keys, kind="stable")
+    assert np.array_equal(k, keys[order])
+    assert np.array_equal(v, vals[order])
+
+
+def test_radix_sort_edge_patterns(gpu_ctx):
+    n = 10000
+    for keys in (np.zeros(n, np.uint64), np.full(n, 0xFFFFFFFFFFFFFFFF, np.uint64), np.arange(n, dtype=np.uint64)[::-1].copy(),
+                 (np.arange(n, dtype=np.uint64) << np.uint64(56))):
+        k, v = _sort(gpu_ctx, keys, np.arange(n, dtype=np.uint32))
+        order = np.argsort(keys, kind="stable")
+        assert np.array_equal(k, keys[order]) and np.array_equal(v, order.astype(np.uint32))
+
+
+def _scene_bounds(sc):
+    lo, hi = np.full(3, np.inf), np.full(3, -np.inf)
+    for x, mesh, _, _ in sc.instances:
+        p = sc.meshes[mesh][0]["pos"].astype(np.float64)
+        w = p @ np.asarray(x, np.float64)[:3, :3].T + np.asarray(x, np.float64)[:3, 3]
+        lo, hi = np.minimum(lo, w.min(0)), np.maximum(hi, w.max(0))
+    return lo, hi
+
+
+def _random_rays(sc, n, seed):
+    """Origins in the scene box inflated by 50 %, aimed at random points inside the box."""
+    lo, hi = _scene_bounds(sc)
+    c, e = 0.5 * (lo + hi), 0.5 * (hi - lo)
+    rng = np.random.RandomState(seed)
+    o = c + 1.5 * e * (2 * rng.rand(n, 3) - 1)
+    tgt = c + e * (2 * rng.rand(n, 3) - 1)
+    d = tgt - o
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.zeros((n, 8), np.float32)
+    rays[:, :3], rays[:, 4:7] = o, d
+    rays[:, 3], rays[:, 7] = 1e-5, 1e10
+    return rays
+
+
+@pytest.mark.parametrize("builder", [
+    lambda: scenes.cornell_materials(32, 32, env=False, lights="all"),
+    lambda: scenes.instanced_field(32, 32, subdiv=3, grid=5),
+    lambda: scenes.glass_blob(32, 32, subdiv=5, env_size=(16, 8)),
+])
+def test_traversal_matches_oracle_on_random_rays(gpu_ctx, cpu_ctx, builder):
+    sc = builder()
+    sc.upload(gpu_ctx)
+    sc.upload(cpu_ctx)
+    rays = _random_rays(sc, 200000, 5)
+    tg, ig = gpu_ctx.trace_rays(rays)
+    tc, ic = cpu_ctx.trace_rays(rays)
+    same = (ig == ic).all(axis=1)
+    hit = ic[:, 0] != 0xFFFFFFFF
+    assert hit.mean() > 0.2
+    tie = ~same & (np.abs(tg[:, 0] - tc[:, 0]) <= 1e-5 * np.maximum(1.0, np.abs(tc[:, 0])))  # same t, other primitive
+    assert (same | tie).mean() >= 0.999, (same.mean(), tie.mean())
+    ok = same & hit
+    assert (np.abs(tg[ok, 0] - tc[ok, 0]) / np.maximum(1.0, tc[ok, 0])).max() <= 1e-4
+    assert np.quantile(np.abs(tg[ok, 1:] - tc[ok, 1:]).max(axis=1), 0.999) <= 1e-3  # barycentrics (grazing hits are ill-conditioned)
+    # any-hit kernel agrees with "closest hit exists below tmax"
+    rays[:, 7] = np.where(hit, np.maximum(tc[:, 0] * 1.5, 1e-3), 5.0)
+    og, oc = gpu_ctx.occlusion_rays(rays), cpu_ctx.occlusion_rays(rays)
+    assert (og == oc).mean() >= 0.999
+    rays[:, 7] = tc[:, 0] * 0.5  # stop well short of the first hit: nothing may be reported
+    assert gpu_ctx.occlusion_rays(rays)[hit].sum() <= 1e-4 * hit.sum()
+
+
+def test_watertight_on_shared_edges_and_vertices(gpu_ctx):
+    """Rays aimed exactly at mesh vertices and edge midpoints of a closed mesh from outside must hit it."""
+    v, idx = scenes.blob(4, 77, 0.2)
+    sc = host.Scene()
+    sc.set_camera("perspective", 8, 8)
+    sc.add_material("m", scenes.mat(0, diffuse=(.5, .5, .5)))
+    sc.add_mesh("blob", v, idx)
+    sc.add_instance("blob", "m")
+    sc.shots.append(host.Shot((0, 0, 5), (0, 0, 0), (0, 1, 0)))
+    sc.upload(gpu_ctx)
+    from helpers import rays_toward, transversal_targets
+    for origin in ((0.003, -0.002, 6.0), (5.0, 3.0, -2.0), (-4.0, -4.0, 4.0)):
+        targets = transversal_targets(v["pos"], idx, origin)
+        assert len(targets) > 3000
+        _, ip = gpu_ctx.trace_rays(rays_toward(origin, targets))
+        assert (ip[:, 0] != 0xFFFFFFFF).all(), f"{(ip[:, 0] == 0xFFFFFFFF).sum()} rays leaked through shared edges"
+
+
+def test_bvh_build_stats(gpu_ctx):
+    sc = scenes.glass_blob(16, 16, subdiv=6, env_size=(16, 8))
+    ms = sc.upload(gpu_ctx)
+    st = gpu_ctx.accel_stats()
+    n_tris = sum(len(i) // 3 for _, i in sc.meshes)
+    assert st["leaf_prims"] == n_tris and st["nodes"] == sum(max(len(i) // 3 - 1, 1) for _, i in sc.meshes)
+    assert 0 < ms < 1000 and st["sah_cost"] > 0

@@ -1,0 +1,149 @@
+"""Parity tests proper: the CUDA path through the C ABI vs the CPU oracle on the same seeded scenes,
+with the thresholds of BASELINE.json: primary-hit primitive ids agree on >= 99.9 % of pixels,
+AOVs within 1e-4 away from silhouettes, radiance mean relative error <= 1 % and FLIP <= 0.01 at
+equal spp.  RNG streams are shared, so the images agree far tighter than that except where a
+rounding difference flips a branch."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from asuna_b200 import host, metrics, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def silhouette_mask(ids):
+    """Pixels whose 4-neighbourhood sees a different (instance, primitive-instance) -- object edges."""
+    inst = ids[..., 0].astype(np.int64)
+    m = np.zeros(inst.shape, bool)
+    m[:-1] |= inst[:-1] != inst[1:]
+    m[1:] |= inst[:-1] != inst[1:]
+    m[:, :-1] |= inst[:, :-1] != inst[:, 1:]
+    m[:, 1:] |= inst[:, :-1] != inst[:, 1:]
+    return m
+
+
+def compare(sc, gpu, cpu, shot=0):
+    sc.upload(gpu)
+    sc.upload(cpu)
+    sc.begin_shot(gpu, shot)
+    sc.begin_shot(cpu, shot)
+    ig, tg = gpu.trace_primary()
+    ic, tc = cpu.trace_primary()
+    same = (ig == ic).all(axis=2)
+    assert same.mean() >= 0.999, f"primary ids agree on {same.mean():.5f}"
+    assert np.abs(tg - tc)[same].max() <= 1e-4 * max(1.0, float(tc.max()))
+    g = sc.render_shot(gpu, shot)
+    c = sc.render_shot(cpu, shot)
+    interior = same & ~silhouette_mask(ic)
+    for k in range(1, len(g)):
+        d = np.abs(g[k][..., :3] - c[k][..., :3]).max(axis=2)
+        assert d[interior].max() <= 1e-4, f"AOV {k} differs by {d[interior].max()}"
+        assert np.array_equal(g[k][..., 3], c[k][..., 3])
+    rel = metrics.mean_relative_error(g[0], c[0])
+    fl = metrics.flip(g[0], c[0])
+    assert rel <= 0.01, f"mean relative error {rel}"
+    assert fl <= 0.01, f"FLIP {fl}"
+    assert np.array_equal(g[0][..., 3], c[0][..., 3])
+    sg, so = gpu.stats(), cpu.stats()
+    assert abs(sg["closest_rays"] - so["closest_rays"]) <= 1e-3 * so["closest_rays"]
+    nz = cpu.traversal_counters()["shadow_rays_nonzero"]  # the GPU skips zero-radiance shadow rays (A.3-4)
+    assert abs(sg["shadow_rays"] - nz) <= 1e-3 * max(nz, 1)
+    return rel, fl
+
+
+SCENES = {
+    "cornell": lambda: scenes.cornell(96, 96, spp=8, depth=5),
+    "materials_all_lights": lambda: scenes.cornell_materials(96, 72, spp=8, env=False, lights="all", textured=True),
+    "materials_env": lambda: scenes.cornell_materials(96, 72, spp=8, env=True, lights="rect", textured=True),
+    "materials_env_only": lambda: scenes.cornell_materials(64, 48, spp=8, env=True, lights="none", textured=False),
+    "materials_point": lambda: scenes.cornell_materials(64, 48, spp=8, env=False, lights="point", textured=False),
+    "materials_distant_mesh": lambda: scenes.cornell_materials(64, 48, spp=8, env=False, lights="mesh", textured=True),
+    "glass_blob": lambda: scenes.glass_blob(128, 72, spp=8, depth=8, subdiv=4, env_size=(128, 64)),
+    "pbr_sunsky": lambda: scenes.pbr_spheres(128, 72, spp=8, depth=5, subdiv=4, tex_size=64),
+    "instanced_field": lambda: scenes.instanced_field(128, 72, spp=8, depth=5, subdiv=3, grid=4),
+}
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_render_parity(name, gpu_ctx, cpu_ctx):
+    compare(SCENES[name](), gpu_ctx, cpu_ctx)
+
+
+def test_depth_of_field_and_opencv_cameras(gpu_ctx, cpu_ctx, product_lib, oracle_lib):
+    from asuna_b200 import capi
+    from oracle.binding import OracleContext
+    sc = scenes.cornell(80, 60, spp=6, depth=4)
+    sc.camera["aperture"], sc.camera["focal_distance"] = 0.05, 2.0
+    scenes.orbit_shots(sc, 3, (0.5, 0.4, 0.5), 2.2, 0.6)
+    sc.shots[1].state = sc.state.copy()
+    sc.shots[1].state["spp"], sc.shots[1].state["maxPathDepth"] = 3, 2  # per-shot override (scene.cpp:439-453)
+    sc.upload(gpu_ctx)
+    sc.upload(cpu_ctx)
+    for shot in range(3):
+        g, c = sc.render_shot(gpu_ctx, shot), sc.render_shot(cpu_ctx, shot)
+        assert metrics.mean_relative_error(g[0], c[0]) <= 0.01 and metrics.flip(g[0], c[0]) <= 0.01
+    so = scenes.cornell(80, 60, spp=6, depth=4)
+    so.set_camera("opencv", 80, 60, fxfycxcy=[70.0, 70.0, 40.0, 30.0])
+    g2, c2 = capi.Context(product_lib, 0), OracleContext()
+    compare(so, g2, c2)
+
+
+def test_use_face_normal_and_ignore_emissive(gpu_ctx, cpu_ctx):
+    sc = scenes.cornell_materials(64, 48, spp=6, env=False, lights="rect", textured=False)
+    sc.state["useFaceNormal"], sc.state["ignoreEmissive"] = 1, 1
+    compare(sc, gpu_ctx, cpu_ctx)
+
+
+@pytest.mark.parametrize("name,builder", [
+    ("cornell_48_spp4", lambda: scenes.cornell(48, 48, spp=4, depth=5)),
+    ("materials_48x36_spp4", lambda: scenes.cornell_materials(48, 36, spp=4, depth=5, env=False, lights="all", textured=True)),
+    ("materials_env_48x36_spp4", lambda: scenes.cornell_materials(48, 36, spp=4, depth=5, env=True, lights="rect", textured=True)),
+    ("pbr_sunsky_48x27_spp4", lambda: scenes.pbr_spheres(48, 27, spp=4, depth=4, subdiv=3, tex_size=32)),
+])
+def test_against_committed_golden_fixtures(gpu_ctx, name, builder):
+    """Fixtures frozen from the oracle by tools/make_golden.py; this test needs no oracle at run time."""
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sc = builder()
+    sc.upload(gpu_ctx)
+    imgs = sc.render_shot(gpu_ctx, 0)
+    sc.begin_shot(gpu_ctx, 0)
+    ids, t = gpu_ctx.trace_primary()
+    assert (ids == g["ids"]).all(axis=2).mean() >= 0.999
+    interior = (ids == g["ids"]).all(axis=2) & ~silhouette_mask(g["ids"])
+    for k in range(len(g["aov"])):
+        d = np.abs(imgs[1 + k][..., :3] - g["aov"][k][..., :3]).max(axis=2)
+        assert d[interior].max() <= 1e-4
+    assert metrics.mean_relative_error(imgs[0], g["radiance"]) <= 0.01
+    assert metrics.flip(imgs[0], g["radiance"]) <= 0.01
+    st = gpu_ctx.stats()
+    assert abs(st["closest_rays"] - int(g["closest_rays"])) <= max(2, 1e-3 * int(g["closest_rays"]))
+
+
+def test_closed_forms_on_gpu(gpu_ctx):
+    sc = scenes.cornell(32, 32, spp=2, depth=3)
+    sc.state["bgColor"] = (0.25, 0.5, 0.75)
+    sc.shots[0] = host.Shot((0.5, 0.5, 2.4), (0.5, 3.0, 2.4), (0, 0, 1))
+    sc.upload(gpu_ctx)
+    img = sc.render_shot(gpu_ctx, 0)[0]
+    assert np.allclose(img[..., :3], [0.25, 0.5, 0.75], atol=1e-6)
+    sc.shots[0] = host.Shot((0.5, 0.3, 0.5), (0.5, 0.999, 0.5), (0, 0, 1))
+    img = sc.render_shot(gpu_ctx, 0)[0]
+    assert np.allclose(img[16, 16, :3], [10, 10, 4], atol=1e-4)
+
+
+def test_error_behaviour(gpu_ctx):
+    from asuna_b200 import capi, structs as S
+    with pytest.raises(capi.AsunaError):
+        gpu_ctx.render_frames(1)  # nothing uploaded
+    m = S.default_material()
+    m["type"] = S.MAT_DISNEY
+    with pytest.raises(capi.AsunaError):
+        gpu_ctx.add_material(m)  # outside the hot-path scope
+    v = host.make_vertices([[0, 0, 0], [1, 0, 0], [0, 1, 0]])
+    with pytest.raises(capi.AsunaError):
+        gpu_ctx.add_mesh(v, [0, 1, 3])  # index out of range
+    with pytest.raises(capi.AsunaError):
+        gpu_ctx.add_instance(np.eye(4, dtype=np.float32).reshape(-1), 5, 0)
