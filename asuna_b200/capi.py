@@ -21,7 +21,7 @@ ABI_SYMBOLS = (
     "abi_sizes", "create", "destroy", "last_error", "set_film", "add_texture", "set_envmap", "add_mesh",
     "add_material", "set_lights", "add_instance", "build_accel", "set_camera", "set_sunsky", "set_state",
     "reset_frame", "render_frames", "set_partition", "sync", "read_channel", "export_partial",
-    "import_partial", "channel_device_ptr", "get_stats", "reset_stats", "trace_primary", "trace_rays",
+    "import_partial", "channel_device_ptr", "stream_handle", "set_counting", "get_stats", "reset_stats", "trace_primary", "trace_rays",
     "occlusion_rays", "accel_stats")
 
 
@@ -174,10 +174,18 @@ class Context:
         self._call("channel_device_ptr", C.c_int(ch), C.byref(p))
         return p.value
 
+    def stream_handle(self):
+        p = C.c_void_p()
+        self._call("stream_handle", C.byref(p))
+        return p.value or 0
+
+    def set_counting(self, on):
+        return self._call("set_counting", C.c_int(1 if on else 0))
+
     def stats(self):
         s = np.zeros((), S.Stats)
         self._call("get_stats", _ptr(s))
-        return {k: s[k].item() for k in S.Stats.names}
+        return {k: s[k].item() for k in S.Stats.names if k != "pad"}
 
     def reset_stats(self):
         return self._call("reset_stats")

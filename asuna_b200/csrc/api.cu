@@ -80,7 +80,9 @@ struct asuna_ctx {
   // wavefront buffers
   PathState ps{};
   Counters* d_counters = nullptr;
-  Counters* h_counters = nullptr;  // pinned
+  Totals* d_totals = nullptr;
+  Totals* h_totals = nullptr;  // pinned
+  bool counting = false;
   uint32_t path_capacity = 0;
   uint32_t max_batch_frames = 8;
   LaunchDims dims;
@@ -144,7 +146,8 @@ void collect_timers(asuna_ctx* ctx) {
   for (auto& te : ctx->pending) {
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, te.a, te.b) == cudaSuccess) {
-      if (te.kind == 0) ctx->stats.trace_ms += ms;
+      if (te.kind == 0) ctx->stats.trace_ms += ms, ctx->stats.closest_ms += ms;
+      else if (te.kind == 3) ctx->stats.trace_ms += ms, ctx->stats.shadow_ms += ms;
       else if (te.kind == 1) ctx->stats.shade_ms += ms;
       else if (te.kind == 2) ctx->stats.total_ms += ms;
     }
@@ -291,7 +294,9 @@ int asuna_create(asuna_ctx** out, int gpu_id) {
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&ctx->d_counters, sizeof(Counters)) != cudaSuccess ||
-      cudaMallocHost(&ctx->h_counters, sizeof(Counters)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_totals, sizeof(Totals)) != cudaSuccess ||
+      cudaMemset(ctx->d_totals, 0, sizeof(Totals)) != cudaSuccess ||
+      cudaMallocHost(&ctx->h_totals, sizeof(Totals)) != cudaSuccess ||
       query_launch_dims(ctx->dims, ctx->sm_count) != cudaSuccess) {
     delete ctx;
     return ASUNA_E_CUDA;
@@ -323,11 +328,12 @@ void asuna_destroy(asuna_ctx* ctx) {
   for (auto& p : ctx->out.img) free_dev(p);
   free_dev(ctx->d_partial);
   free_dev(ctx->d_counters);
+  free_dev(ctx->d_totals);
   free_dev(ctx->d_user_rays);
   free_dev(ctx->d_user_tuv);
   free_dev(ctx->d_user_ip);
   free_dev(ctx->d_user_occ);
-  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
   ctx->scratch.release();
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -605,16 +611,18 @@ static int render_batch(asuna_ctx* ctx, const int* frames, uint32_t n_frames) {
   auto bounce = [&]() {
     {
       ScopedTimer t(ctx, 0);
-      launch_trace_closest(s, ctx->dims, ctx->view, ctx->ps, ctx->d_counters, iter, qsel);
+      launch_trace_closest(s, ctx->dims, ctx->view, ctx->ps, ctx->d_counters, iter, qsel, ctx->counting);
     }
     {
       ScopedTimer t(ctx, 1);
       launch_shade(s, ctx->dims, ctx->view, fp, ctx->ps, ctx->out, ctx->d_counters, iter, qsel);
     }
     {
-      ScopedTimer t(ctx, 0);
+      ScopedTimer t(ctx, 3);
       launch_trace_shadow(s, ctx->dims, ctx->view, ctx->ps, ctx->d_counters, iter);
     }
+    ctx->stats.kernel_launches += 3;
+    ctx->stats.closest_launches += 1;
     iter++;
     qsel ^= 1;
   };
@@ -633,15 +641,8 @@ static int render_batch(asuna_ctx* ctx, const int* frames, uint32_t n_frames) {
     ScopedTimer t(ctx, 1);
     launch_accumulate(s, fp, ctx->ps, ctx->out);
   }
-  // ray statistics of this batch: summed on the host after the async copy lands (stream order)
-  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_counters, ctx->d_counters, sizeof(Counters), cudaMemcpyDeviceToHost, s));
-  ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
-  for (int i = 0; i <= iter && i <= ASUNA_MAX_ITERS; i++) {
-    if (i < iter) ctx->stats.closest_rays += ctx->h_counters->queue[i];
-    if (i < iter) ctx->stats.shadow_rays += ctx->h_counters->shadow[i];
-    if (i < iter) ctx->stats.incoherent_closest_rays += ctx->h_counters->incoherent[i];
-  }
-  if (ctx->h_counters->stack_overflow) return fail(ctx, ASUNA_E_CUDA, "traversal stack overflow");
+  launch_fold_counters(s, ctx->d_counters, ctx->d_totals, iter);
+  ctx->stats.kernel_launches += 3;  // raygen, accumulate, fold
   ctx->stats.paths += n_paths;
   ctx->have_accum = true;
   ASUNA_CUDA_CHECK(cudaGetLastError());
@@ -669,10 +670,13 @@ int asuna_render_frames(asuna_ctx* ctx, uint32_t n) {
   return 0;
 }
 
+static int pull_totals(asuna_ctx* ctx);
+
 int asuna_sync(asuna_ctx* ctx) {
   cudaSetDevice(ctx->device);
-  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-  collect_timers(ctx);
+  int rc = pull_totals(ctx);  // also surfaces a traversal stack overflow
+  if (rc) return rc;
+  ASUNA_CUDA_CHECK(cudaGetLastError());
   return 0;
 }
 
@@ -707,11 +711,31 @@ int asuna_channel_device_ptr(asuna_ctx* ctx, int ch, void** out) {
   return 0;
 }
 
+static int pull_totals(asuna_ctx* ctx) {
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->h_totals, ctx->d_totals, sizeof(Totals), cudaMemcpyDeviceToHost, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
+  ctx->stats.closest_rays = ctx->h_totals->closest_rays;
+  ctx->stats.shadow_rays = ctx->h_totals->shadow_rays;
+  ctx->stats.incoherent_closest_rays = ctx->h_totals->incoherent_rays;
+  ctx->stats.node_visits = ctx->h_totals->node_visits;
+  ctx->stats.tri_tests = ctx->h_totals->tri_tests;
+  if (ctx->h_totals->stack_overflow) return fail(ctx, ASUNA_E_CUDA, "traversal stack overflow: results are incomplete");
+  return 0;
+}
+
 int asuna_get_stats(asuna_ctx* ctx, AsunaStats* out) {
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
-  collect_timers(ctx);
+  int rc = pull_totals(ctx);
   *out = ctx->stats;
+  return rc;
+}
+int asuna_stream_handle(asuna_ctx* ctx, void** out) {
+  *out = (void*)ctx->stream;
+  return 0;
+}
+int asuna_set_counting(asuna_ctx* ctx, int on) {
+  ctx->counting = on != 0;
   return 0;
 }
 int asuna_reset_stats(asuna_ctx* ctx) {
@@ -721,6 +745,7 @@ int asuna_reset_stats(asuna_ctx* ctx) {
   float b = ctx->stats.build_ms;
   ctx->stats = AsunaStats{};
   ctx->stats.build_ms = b;
+  ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->d_totals, 0, sizeof(Totals), ctx->stream));
   return 0;
 }
 

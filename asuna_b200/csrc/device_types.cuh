@@ -97,6 +97,14 @@ struct Counters {
   uint32_t ticket_closest[ASUNA_MAX_ITERS + 1];  // dynamic work-fetch tickets of the persistent trace kernels
   uint32_t ticket_shadow[ASUNA_MAX_ITERS + 1];
   uint32_t stack_overflow;
+  unsigned long long node_visits;   // instrumented traversal only (asuna_set_counting)
+  unsigned long long tri_tests;
+};
+
+// Totals folded from `Counters` at the end of every batch by k_fold_counters (no host sync needed).
+struct Totals {
+  unsigned long long closest_rays, shadow_rays, incoherent_rays, node_visits, tri_tests;
+  unsigned long long stack_overflow;
 };
 
 struct FrameParams {

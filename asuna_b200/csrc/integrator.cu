@@ -104,9 +104,9 @@ ADEV bool hit_triangle(const RaySpace& r, float3 v0, float3 v1, float3 v2, float
 // Two-level traversal with traceRayEXT semantics: per instance the ray is taken into object space
 // (origin and unnormalised direction through world->object), t is shared between spaces.
 // Ties are broken toward the lower (instance, primitive) pair, as the oracle defines.
-template <bool ANY>
+template <bool ANY, bool COUNT = false>
 __device__ bool traverse(const SceneView& sc, float3 wo, float3 wd, float tmin, float tmax, HitRec& best,
-                         uint32_t* overflow) {
+                         uint32_t* overflow, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
   if (sc.n_instances == 0) return false;
   int stack[kStackSize];
   int sp = 0;
@@ -118,6 +118,7 @@ __device__ bool traverse(const SceneView& sc, float3 wo, float3 wd, float tmin, 
   for (;;) {
     if (cur >= 0) {
       const BvhNode* np = (in_blas ? sc.blas_nodes : sc.tlas_nodes) + cur;
+      if (COUNT) (*n_nodes)++;
       float4 a = __ldg(&np->c0xy), b = __ldg(&np->c1xy), z = __ldg(&np->cz);
       int4 link = __ldg(&np->link);
       float t0, t1;
@@ -145,6 +146,7 @@ __device__ bool traverse(const SceneView& sc, float3 wo, float3 wd, float tmin, 
           const TriSlot* tp = sc.tris + first + k;
           float4 v0 = __ldg(&tp->v0), v1 = __ldg(&tp->v1), v2 = __ldg(&tp->v2);
           float t, b1, b2;
+          if (COUNT) (*n_tris)++;
           if (!hit_triangle(rs, f3(v0), f3(v1), f3(v2), t, b1, b2)) continue;
           if (!(t > tmin)) continue;
           uint32_t prim = __float_as_uint(v0.w);
@@ -185,11 +187,13 @@ __device__ bool traverse(const SceneView& sc, float3 wo, float3 wd, float tmin, 
 }
 
 // ---- trace kernels: persistent, warp-granular dynamic fetch -----------------------------------
+template <bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads)
 k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter, int qsel) {
   const uint32_t count = cnt->queue[iter];
   const uint32_t* queue = ps.queue[qsel];
   const int lane = threadIdx.x & 31;
+  uint32_t n_nodes = 0, n_tris = 0;
   for (;;) {
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(&cnt->ticket_closest[iter], 32u);
@@ -201,10 +205,32 @@ k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cn
       float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
       HitRec h;
       h.inst = 0xFFFFFFFFu, h.prim = 0xFFFFFFFFu, h.b1 = h.b2 = h.t = 0.f;
-      traverse<false>(sc, f3(o), f3(d), kMinimum, kInfinity, h, &cnt->stack_overflow);
+      traverse<false, COUNT>(sc, f3(o), f3(d), kMinimum, kInfinity, h, &cnt->stack_overflow, &n_nodes, &n_tris);
       ps.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), h.inst, h.prim);
     }
   }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, o);
+      n_tris += __shfl_xor_sync(0xFFFFFFFFu, n_tris, o);
+    }
+    if (lane == 0) {
+      atomicAdd(&cnt->node_visits, (unsigned long long)n_nodes);
+      atomicAdd(&cnt->tri_tests, (unsigned long long)n_tris);
+    }
+  }
+}
+
+// Adds one batch's per-iteration counters into the persistent totals (one thread; a few hundred words).
+__global__ void k_fold_counters(const Counters* cnt, Totals* tot, int iters) {
+  unsigned long long c = 0, s = 0, inc = 0;
+  for (int i = 0; i < iters; i++) c += cnt->queue[i], s += cnt->shadow[i], inc += cnt->incoherent[i];
+  tot->closest_rays += c;
+  tot->shadow_rays += s;
+  tot->incoherent_rays += inc;
+  tot->node_visits += cnt->node_visits;
+  tot->tri_tests += cnt->tri_tests;
+  tot->stack_overflow += cnt->stack_overflow;
 }
 
 __global__ void __launch_bounds__(kTraceThreads) k_trace_shadow(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter) {
@@ -495,8 +521,12 @@ void launch_raygen(cudaStream_t s, const FrameParams& fp, const PathState& ps, c
   k_raygen<<<div_up(total, 256), 256, 0, s>>>(fp, ps, out, cnt);
 }
 void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
-                          int iter, int qsel) {
-  k_trace_closest<<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+                          int iter, int qsel, bool counting) {
+  if (counting) k_trace_closest<true><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+  else k_trace_closest<false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+}
+void launch_fold_counters(cudaStream_t s, const Counters* cnt, Totals* tot, int iters) {
+  k_fold_counters<<<1, 1, 0, s>>>(cnt, tot, iters);
 }
 void launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const FrameParams& fp, const PathState& ps,
                   const OutputImages& out, Counters* cnt, int iter, int qsel) {
@@ -525,7 +555,7 @@ void launch_trace_user(cudaStream_t s, const SceneView& sc, const float4* rays, 
 
 cudaError_t query_launch_dims(LaunchDims& ld, int sm_count) {
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest, kTraceThreads, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest<false>, kTraceThreads, 0);
   if (e != cudaSuccess) return e;
   ld.trace_blocks = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, kShadeThreads, 0);

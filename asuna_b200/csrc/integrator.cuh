@@ -17,7 +17,8 @@ cudaError_t query_launch_dims(LaunchDims& ld, int sm_count);
 
 void launch_raygen(cudaStream_t s, const FrameParams& fp, const PathState& ps, const OutputImages& out, Counters* cnt);
 void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
-                          int iter, int qsel);
+                          int iter, int qsel, bool counting);
+void launch_fold_counters(cudaStream_t s, const Counters* cnt, Totals* tot, int iters);
 void launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const FrameParams& fp, const PathState& ps,
                   const OutputImages& out, Counters* cnt, int iter, int qsel);
 void launch_trace_shadow(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,

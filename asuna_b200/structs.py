@@ -41,8 +41,9 @@ SunSky = np.dtype([  # sun_and_sky.h:6-28
 
 Stats = np.dtype([
     ("paths", np.uint64), ("closest_rays", np.uint64), ("shadow_rays", np.uint64),
-    ("incoherent_closest_rays", np.uint64), ("trace_ms", f4), ("shade_ms", f4), ("total_ms", f4),
-    ("build_ms", f4)])
+    ("incoherent_closest_rays", np.uint64), ("kernel_launches", np.uint64), ("closest_launches", np.uint64),
+    ("node_visits", np.uint64), ("tri_tests", np.uint64), ("trace_ms", f4), ("shade_ms", f4), ("total_ms", f4),
+    ("build_ms", f4), ("closest_ms", f4), ("shadow_ms", f4), ("pad", f4, 2)])
 
 EXPECTED_SIZES = (44, 132, 76, 224, 84, 96)
 assert (Vertex.itemsize, Material.itemsize, Light.itemsize, Camera.itemsize, State.itemsize,

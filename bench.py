@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the asuna_b200 hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference --steps K --warmup W    (CPU oracle on the host cores, same config)
+
+Metric (BASELINE.json): 1080p samples/sec (pixel-samples per second) on config[1] -- the glass blob:
+dielectric BSDF + env-map light, 1920x1080, max path depth 8.  One *step* is one pass of the hot path
+over one batch of `--frames-per-step` 1-spp frames per GPU (raygen -> [trace, shade, shadow] x depth ->
+accumulate).  Multi-GPU is the sample-range split of SURVEY.md 8e: rank r renders the frames
+f % N == r of the shot (weak scaling: frames per GPU fixed), the (sum w*L, sum w) planes are summed to
+rank 0 with one NCCL reduce and resolved there.
+
+`value`   : device-resident throughput -- scene + BVH already in HBM, K steps bracketed by barrier +
+            synchronize, CUDA events on the library's stream, max over ranks (+ the one NCCL reduce at N>1).
+`e2e`     : the same metric through the reference-facing C ABI with HOST buffers: every step uploads the
+            step's camera / state / sun-sky structs from host memory, renders, resolves (NCCL reduce at
+            N > 1) and reads the radiance image back into host memory (a complete mini-shot).
+`roofline`: closest-hit trace kernel (dominant): algorithmic bytes per ray (32 B ray in +
+            16 B hit out + visited nodes x 64 B + tested triangles x 48 B, counts from an untimed
+            instrumented pass over the same BVH) x rays per launch / mean launch time (CUDA events).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "1080p samples/sec"
+UNIT = "samples/s"
+WORKLOAD = "glass blob (dielectric + env-map), 1920x1080, depth 8 [BASELINE.json configs[1]]"
+NODE_BYTES, TRI_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 64, 48, 32, 16
+
+
+def build_scene(args):
+    from asuna_b200 import scenes
+    return scenes.glass_blob(args.width, args.height, spp=256, depth=8, subdiv=args.subdiv, env_size=(2048, 1024))
+
+
+def n_triangles(args):
+    return 20 * 4 ** args.subdiv + 2 * 128 * (2 * 65 - 1) - 2 * 128 + 128  # blob + lathe bowl (minus pole slivers) + ground
+
+
+def config_dict(args, n_gpus):
+    return {"workload": WORKLOAD, "width": args.width, "height": args.height, "max_path_depth": 8,
+            "triangles": n_triangles(args), "frames_per_step_per_gpu": args.frames_per_step,
+            "parallelism": f"sample-range split x{n_gpus}, scene replicated",
+            "cache_policy": "inputs larger than L2: per-step path state ~%.1f GB per GPU" %
+                            (args.width * args.height * args.frames_per_step * 148 / 1e9)}
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.QUERY,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for n, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except (ValueError, IndexError):
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("k_trace_closest_dram_bytes_per_launch")
+    return None
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_run(args, steps, warmup, budget_s=None):
+    """Times the CPU oracle (a port of the reference shaders; the reference itself needs a Vulkan RT device
+    and cannot run here) on the same workload.  A step is one 1-spp 1080p frame."""
+    from oracle.binding import OracleContext
+    sc = build_scene(args)
+    ctx = OracleContext()
+    cores = os.cpu_count() or 1
+    sc.upload(ctx)
+    sc.begin_shot(ctx, 0)
+    for _ in range(warmup):
+        ctx.render_frames(1)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        ctx.render_frames(1)
+        done += 1
+        if budget_s and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    samples = done * args.width * args.height
+    st = ctx.stats()
+    ctx.close()
+    return {"value": samples / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{done} x 1-spp {args.width}x{args.height} frames of the same scene ({dt:.1f} s, BVH build excluded)",
+            "ms_per_step": 1e3 * dt / max(done, 1), "steps": done,
+            "mrays_per_s": (st["closest_rays"] + st["shadow_rays"]) / max(st["total_ms"], 1e-9) / 1e3}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_run(args, max(args.steps, 1), args.warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": r["steps"],
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config_dict(args, args.gpus),
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "mrays_per_s": r["mrays_per_s"], "gpu_launches": 0,
+            "note": "CPU oracle port of the reference shaders on all host threads; one step = one 1-spp frame"}
+    print(json.dumps(line))
+    return 0
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="asuna_b200", choices=["asuna_b200", "reference"])
+    ap.add_argument("--width", type=int, default=1920)
+    ap.add_argument("--height", type=int, default=1080)
+    ap.add_argument("--subdiv", type=int, default=6)
+    ap.add_argument("--frames-per-step", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=12.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from asuna_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    sc = build_scene(args)
+    ctx = capi.Context(gpu_id=local)  # raises without the CUDA library / a device: there is no fallback
+    t0 = time.perf_counter()
+    build_ms = sc.upload(ctx)
+    upload_s = time.perf_counter() - t0
+    ctx.set_partition(rank, world)
+    stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+    n_px = args.width * args.height
+    fps = args.frames_per_step
+    global_frames_per_step = fps * world  # every rank renders fps of them
+
+    class _Ptr:
+        def __init__(self, p, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (p, False), "version": 3}
+
+    def resolve():
+        """Multi-GPU combine: one NCCL reduce of the (sum w*L, sum w) plane to rank 0, then L = sum/w."""
+        if world == 1:
+            return
+        t = torch.as_tensor(_Ptr(ctx.export_partial(), n_px * 4), device=dev)
+        dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
+        torch.cuda.synchronize()
+        if rank == 0:
+            ctx.import_partial()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- untimed instrumented pass: mean nodes / triangles per closest-hit ray on this BVH
+    sc.begin_shot(ctx, 0)
+    ctx.set_counting(True)
+    ctx.reset_stats()
+    ctx.render_frames(world)  # one frame per rank
+    s = ctx.stats()
+    nodes_per_ray = s["node_visits"] / max(s["closest_rays"], 1)
+    tris_per_ray = s["tri_tests"] / max(s["closest_rays"], 1)
+    bytes_per_ray = RAY_IN_BYTES + HIT_OUT_BYTES + nodes_per_ray * NODE_BYTES + tris_per_ray * TRI_BYTES
+    ctx.set_counting(False)
+
+    # ---- device-resident throughput
+    sc.begin_shot(ctx, 0)
+    for _ in range(args.warmup):
+        ctx.render_frames(global_frames_per_step)
+    ctx.sync()
+    ctx.reset_stats()
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev0.record()
+    for _ in range(args.steps):
+        ctx.render_frames(global_frames_per_step)
+    with torch.cuda.stream(stream):
+        ev1.record()
+    ctx.sync()
+    resolve()
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - w0)
+    dev_ms = ev0.elapsed_time(ev1)
+    st = ctx.stats()
+    t = torch.tensor([wall_ms, dev_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_ms, dev_ms = t.tolist()
+    samples = args.steps * global_frames_per_step * n_px
+    value = samples / (wall_ms / 1e3)
+
+    # ---- end to end through the C ABI with host buffers (mini-shot per step)
+    cam_host = sc.gpu_camera(sc.shots[0])
+    h2d = cam_host.nbytes + sc.shot_state(0).nbytes + sc.sunsky.nbytes
+    d2h = n_px * 16
+    for _ in range(2):
+        sc.begin_shot(ctx, 0)
+        ctx.render_frames(global_frames_per_step)
+        resolve()
+    barrier()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        sc.begin_shot(ctx, 0)  # camera + state + sun/sky structs from host memory
+        ctx.render_frames(global_frames_per_step)
+        resolve()
+        if rank == 0:
+            img = ctx.read_channel(0)  # radiance image back into host memory
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - e0)
+    t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = t.item()
+    e2e_value = samples / (e2e_ms / 1e3)
+    clock_info = clocks.stop() if rank == 0 else None
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        rays_per_launch = st["closest_rays"] / max(st["closest_launches"], 1)
+        launch_ms = st["closest_ms"] / max(st["closest_launches"], 1)
+        achieved = bytes_per_ray * rays_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
+        rays = st["closest_rays"] + st["shadow_rays"]
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_dict(args, world),
+            "device_ms_per_step": dev_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": int(st["kernel_launches"]),
+            "clocks": clock_info,
+            "roofline": {"kernel": "k_trace_closest", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
+                         "rays_per_launch": rays_per_launch, "launch_ms": launch_ms,
+                         "kernel_share_of_step": st["closest_ms"] / max(st["total_ms"], 1e-9),
+                         "note": "BVH + triangles (~%.0f MB) are L2-resident, so this kernel is latency/issue-bound; "
+                                 "the HBM fraction is reported as the contract asks" %
+                                 (n_triangles(args) * (NODE_BYTES + TRI_BYTES) / 1e6)},
+            "mrays_per_s_rank0": rays / max(st["trace_ms"], 1e-9) / 1e3,
+            "incoherent_mrays_per_s_rank0": st["incoherent_closest_rays"] / max(st["closest_ms"], 1e-9) / 1e3,
+            "rays_per_sample": rays / max(st["paths"], 1),
+            "bvh_build_ms": build_ms, "scene_upload_s": upload_s,
+            "kernel_ms_rank0": {k: st[k] for k in ("closest_ms", "shadow_ms", "shade_ms", "total_ms")},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_run(args, 64, 1, budget_s=args.cpu_budget_s)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -168,16 +168,24 @@ enum AsunaError {
   ASUNA_E_UNSUPPORTED = -4 /* material type outside the hot-path scope */
 };
 
-/* Counters a caller may read after a render; all are totals since the last reset. */
+/* Counters a caller may read after a render; all are totals since the last asuna_reset_stats.
+ * Times are device times from CUDA events recorded on the context's stream around each launch. */
 typedef struct AsunaStats {
   uint64_t paths;          /* pixel-samples started                         */
   uint64_t closest_rays;   /* closest-hit rays traced (rgen:108)            */
   uint64_t shadow_rays;    /* shadow rays traced (rgen:121)                 */
   uint64_t incoherent_closest_rays; /* closest-hit rays at depth >= 2       */
-  float trace_ms;          /* summed device time of the two trace kernels   */
-  float shade_ms;          /* summed device time of raygen+shade+accumulate */
-  float total_ms;          /* device time of all asuna_render_frames calls  */
-  float build_ms;          /* device time of the last asuna_build_accel     */
+  uint64_t kernel_launches;  /* kernels launched by asuna_render_frames     */
+  uint64_t closest_launches; /* launches of the closest-hit trace kernel    */
+  uint64_t node_visits;    /* BVH nodes fetched by closest-hit rays (only with asuna_set_counting) */
+  uint64_t tri_tests;      /* triangle tests by closest-hit rays   (only with asuna_set_counting) */
+  float trace_ms;          /* closest-hit + shadow trace kernels            */
+  float shade_ms;          /* raygen + shade + accumulate kernels           */
+  float total_ms;          /* whole batches, launch gaps included           */
+  float build_ms;          /* the last asuna_build_accel                    */
+  float closest_ms;        /* closest-hit trace kernel alone                */
+  float shadow_ms;         /* shadow trace kernel alone                     */
+  float pad[2];
 } AsunaStats;
 
 typedef struct asuna_ctx asuna_ctx; /* opaque */
@@ -250,6 +258,12 @@ int asuna_import_partial(asuna_ctx* ctx);
 
 /* Device pointer of output image `channel` (w*h float4), for zero-copy consumers. */
 int asuna_channel_device_ptr(asuna_ctx* ctx, int channel, void** out_device_ptr);
+
+/* CUstream the context launches on (so a caller can bracket work with its own events). */
+int asuna_stream_handle(asuna_ctx* ctx, void** out_stream);
+/* Instrumented traversal: when on, closest-hit launches also count node visits / triangle tests
+ * (slower; used to derive the algorithmic bytes per ray of the roofline, never while timing). */
+int asuna_set_counting(asuna_ctx* ctx, int on);
 
 int asuna_get_stats(asuna_ctx* ctx, AsunaStats* out);
 int asuna_reset_stats(asuna_ctx* ctx);

@@ -1354,6 +1354,7 @@ int oracle_import_partial(oracle_ctx* c) {
 int oracle_get_stats(oracle_ctx* c, AsunaStats* s) {
   c->stats.closest_rays = c->n_closest, c->stats.shadow_rays = c->n_shadow;
   c->stats.incoherent_closest_rays = c->n_incoherent;
+  c->stats.node_visits = c->n_node_visits, c->stats.tri_tests = c->n_tri_tests;
   *s = c->stats;
   return 0;
 }
