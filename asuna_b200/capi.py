@@ -213,4 +213,4 @@ class Context:
     def accel_stats(self):
         out = (C.c_uint64 * 4)()
         self._call("accel_stats", out)
-        return {"nodes": out[0], "leaf_prims": out[1], "max_depth": out[2], "sah_cost": out[3] / 1000.0}
+        return {"nodes": out[0], "leaf_prims": out[1], "tlas_nodes": out[2], "sah_cost": out[3] / 1000.0}

@@ -54,7 +54,8 @@ struct asuna_ctx {
   bool scene_dirty = true;
 
   // device scene
-  BvhNode *d_blas_nodes = nullptr, *d_tlas_nodes = nullptr;
+  WideNode *d_blas_nodes = nullptr, *d_tlas_nodes = nullptr;
+  BuildResult* d_build_results = nullptr;
   TriSlot* d_tris = nullptr;
   uint32_t* d_tlas_leaf_inst = nullptr;
   DInstance* d_instances = nullptr;
@@ -169,6 +170,7 @@ void free_scene_device(asuna_ctx* ctx) {
   free_dev(ctx->d_textures);
   free_dev(ctx->d_mesh_lo);
   free_dev(ctx->d_mesh_hi);
+  free_dev(ctx->d_build_results);
 }
 
 void free_path_buffers(asuna_ctx* ctx) {
@@ -462,9 +464,10 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   if (total_tris >= (1u << 27)) return fail(ctx, ASUNA_E_INVALID, "more than 2^27 triangles");
   uint32_t n_inst = (uint32_t)ctx->instances.size(), n_mesh = (uint32_t)ctx->meshes.size();
   ASUNA_CUDA_CHECK(ctx->scratch.reserve(max_prims));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_blas_nodes, total_nodes * sizeof(BvhNode)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_blas_nodes, total_nodes * sizeof(WideNode)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_build_results, (n_mesh + 1) * sizeof(BuildResult)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tris, total_tris * sizeof(TriSlot)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_nodes, std::max<uint32_t>(n_inst - 1, 1) * sizeof(BvhNode)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_nodes, std::max<uint32_t>(n_inst - 1, 1) * sizeof(WideNode)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_leaf_inst, n_inst * sizeof(uint32_t)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_instances, n_inst * sizeof(DInstance)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_meshes, n_mesh * sizeof(DMesh)));
@@ -503,17 +506,24 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   cudaEventRecord(e0, s);
-  // bottom level: one BVH per mesh (≙ createBottomLevelAS)
+  // bottom level: one wide BVH per mesh (≙ createBottomLevelAS)
   for (uint32_t i = 0; i < n_mesh; i++) {
     HostMesh& m = ctx->meshes[i];
     launch_tri_boxes(s, m.d_vertices, m.d_indices, m.n_tris, ctx->scratch);
-    launch_lbvh(s, m.n_tris, ctx->d_blas_nodes, m.node_base, m.tri_base, ctx->scratch, ctx->d_mesh_lo + i, ctx->d_mesh_hi + i);
-    launch_emit_tris(s, m.d_vertices, m.d_indices, m.n_tris, ctx->scratch.vals[0], ctx->d_tris + m.tri_base);
+    PrimPayload pl;
+    pl.vertices = m.d_vertices, pl.indices = m.d_indices, pl.tris = ctx->d_tris;
+    ASUNA_CUDA_CHECK(launch_build_wide(s, m.n_tris, ctx->d_blas_nodes, (uint32_t)m.node_base, (uint32_t)m.tri_base, ctx->scratch,
+                                       pl, 0.3f, ctx->d_mesh_lo + i, ctx->d_mesh_hi + i, ctx->d_build_results + i));
   }
-  // top level over the instance boxes (≙ createTopLevelAS)
+  // top level over the instance boxes (≙ createTopLevelAS); entering an instance costs a ray transform
+  // plus a whole mesh BVH, so leaves are kept to single instances wherever the SAH allows
   launch_instance_boxes(s, ctx->d_instances, ctx->d_mesh_lo, ctx->d_mesh_hi, n_inst, ctx->scratch);
-  launch_lbvh(s, n_inst, ctx->d_tlas_nodes, 0, 0, ctx->scratch, nullptr, nullptr);
-  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tlas_leaf_inst, ctx->scratch.vals[0], n_inst * sizeof(uint32_t), cudaMemcpyDeviceToDevice, s));
+  {
+    PrimPayload pl;
+    pl.leaf_inst = ctx->d_tlas_leaf_inst;
+    ASUNA_CUDA_CHECK(launch_build_wide(s, n_inst, ctx->d_tlas_nodes, 0, 0, ctx->scratch, pl, 4.0f, nullptr, nullptr,
+                                       ctx->d_build_results + n_mesh));
+  }
   cudaEventRecord(e1, s);
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
   ASUNA_CUDA_CHECK(cudaGetLastError());
@@ -524,19 +534,16 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   ctx->stats.build_ms = ms;
   if (out_ms) *out_ms = ms;
 
-  // SAH cost of the emitted BLASes (for asuna_accel_stats); normalised by each root's half area on the host side
+  // statistics for asuna_accel_stats: wide nodes in use, primitive slots, SAH cost summed over the BLASes
   {
-    double* d_cost = nullptr;
-    ASUNA_CUDA_CHECK(cudaMalloc(&d_cost, sizeof(double)));
-    ASUNA_CUDA_CHECK(cudaMemsetAsync(d_cost, 0, sizeof(double), s));
-    launch_sah_cost(s, ctx->d_blas_nodes, 0, (int)total_nodes, d_cost);
+    std::vector<BuildResult> res(n_mesh + 1);
+    ASUNA_CUDA_CHECK(cudaMemcpy(res.data(), ctx->d_build_results, res.size() * sizeof(BuildResult), cudaMemcpyDeviceToHost));
+    uint64_t nodes = 0, prims = 0;
     double cost = 0.0;
-    ASUNA_CUDA_CHECK(cudaMemcpyAsync(&cost, d_cost, sizeof(double), cudaMemcpyDeviceToHost, s));
-    ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
-    cudaFree(d_cost);
-    ctx->accel_stats[0] = total_nodes;
-    ctx->accel_stats[1] = total_tris;
-    ctx->accel_stats[2] = 0;
+    for (uint32_t i = 0; i < n_mesh; i++) nodes += res[i].wide_nodes, prims += res[i].prim_slots, cost += res[i].sah_cost;
+    ctx->accel_stats[0] = nodes;
+    ctx->accel_stats[1] = prims;
+    ctx->accel_stats[2] = res[n_mesh].wide_nodes;
     ctx->accel_stats[3] = (uint64_t)(cost * 1000.0);
   }
 

@@ -5,14 +5,21 @@
 // ext/nvpro_core/nvvk/raytraceKHR_vk.cpp:77-183,302-376, called from
 // src/pipeline/pipeline_raytrace.cpp:107-147).  Pipeline per BVH (all on one stream, no host sync):
 //   prim boxes + bounds reduce -> 63-bit Morton keys -> LSD radix sort (8 x 8-bit, stable,
-//   histogram / scan / warp-multisplit scatter) -> Karras 2012 LBVH hierarchy -> bottom-up box
-//   fit (atomic arrival flags) -> emit 64-byte child-box nodes + leaf-ordered triangle slots.
+//   histogram / scan / warp-multisplit scatter) -> PLOC (Meister & Bittner 2018: parallel locally-
+//   ordered agglomerative clustering along the Morton curve, one cooperative kernel) which also
+//   fills, at every merge, the SAH dynamic-programming table of Ylitie et al. 2017 -> top-down
+//   collapse into compressed 8-wide nodes (80 B, octant-ordered slots, 8-bit quantised child
+//   boxes) with the primitive slots written in leaf order (second cooperative kernel).
 // Everything is HBM-bound streaming work: loads are coalesced 16-byte where the input layout
 // allows (the 44-byte vertex stride of the wire format does not), grids are sized from n.
+#include <cooperative_groups.h>
+
 #include <algorithm>
 #include <cfloat>
 
 #include "bvh_build.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace asuna {
 
@@ -238,144 +245,447 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const uint64_t* __res
   }
 }
 
-// ---- 4. LBVH hierarchy (Karras 2012) ---------------------------------------------------------
-__device__ __forceinline__ int key_delta(const uint64_t* __restrict__ keys, int n, int i, int j) {
-  if (j < 0 || j >= n) return -1;
-  uint64_t a = keys[i], b = keys[j];
-  if (a == b) return 64 + __clz(i ^ j);
-  return __clzll((long long)(a ^ b));
-}
+// ---- 4. PLOC: binary hierarchy by locally-ordered clustering + SAH collapse table ------------
+// Binary-node numbering during the build: leaf j (sorted position) is n-1+j; inner nodes are handed
+// out from n-2 downwards in merge order, so the last merge -- the root -- is node 0.
+constexpr int kPlocRadius = 10;
+constexpr uint64_t kDecLeaf = 1ull;
 
-// Node numbering during the build: inner nodes 0..n-2 (root 0), leaf j is n-1+j.
-__global__ void k_lbvh_hierarchy(const uint64_t* __restrict__ keys, int n, int2* __restrict__ children,
-                                 int* __restrict__ parent) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1) return;
-  int d = (key_delta(keys, n, i, i + 1) - key_delta(keys, n, i, i - 1)) >= 0 ? 1 : -1;
-  int dmin = key_delta(keys, n, i, i - d);
-  int lmax = 2;
-  while (key_delta(keys, n, i, i + lmax * d) > dmin) lmax <<= 1;
-  int l = 0;
-  for (int t = lmax >> 1; t >= 1; t >>= 1)
-    if (key_delta(keys, n, i, i + (l + t) * d) > dmin) l += t;
-  int j = i + l * d;
-  int dnode = key_delta(keys, n, i, j);
-  int s = 0;
-  for (int t = (l + 1) >> 1;; t = (t + 1) >> 1) {
-    if (key_delta(keys, n, i, i + (s + t) * d) > dnode) s += t;
-    if (t == 1) break;
-  }
-  int gamma = i + s * d + min(d, 0);
-  int left = (min(i, j) == gamma) ? (n - 1 + gamma) : gamma;
-  int right = (max(i, j) == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
-  children[i] = make_int2(left, right);
-  parent[left] = i;
-  parent[right] = i;
-  if (i == 0) parent[0] = -1;
-}
+struct PlocParams {
+  int n;
+  float cost_node, cost_prim;
+  const float4* blo;   // primitive boxes
+  const float4* bhi;
+  const uint32_t* order;  // sorted position -> primitive id
+  float4* nlo;         // [2n-1] binary-node boxes, lo.w = primitive count (bits)
+  float4* nhi;
+  int2* children;      // [n-1]
+  float* cost;         // [2n-1][7]  C(node, i): cheapest forest of <= i wide-BVH roots
+  uint64_t* dec;       // [2n-1]    argmin bookkeeping of the table
+  int* cid[2];         // cluster arrays (ping-pong): binary node id ...
+  float4* clo[2];      // ... and its box, kept in cluster order so the neighbour search streams
+  float4* chi[2];
+  int* nn;             // nearest neighbour of cluster i within the radius
+  uint2* pre;          // per-cluster exclusive prefix inside its block chunk {survivors, merges}
+  uint2* block_sums;   // per block {survivors, merges}
+};
 
-// ---- 5. bottom-up fit: second arrival at a node merges its children ---------------------------
-__global__ void k_lbvh_fit(const float4* __restrict__ blo, const float4* __restrict__ bhi,
-                           const uint32_t* __restrict__ order, int n, const int2* __restrict__ children,
-                           const int* __restrict__ parent, float4* nlo, float4* nhi, uint32_t* flags) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  uint32_t prim = order[j];
-  float4 lo = blo[prim], hi = bhi[prim];
-  int node = n - 1 + j;
-  nlo[node] = lo;
-  nhi[node] = hi;
-  __threadfence();
-  int p = parent[node];
-  while (p >= 0) {
-    if (atomicAdd(&flags[p], 1u) == 0u) return;  // first arrival: the sibling will carry on
-    __threadfence();
-    int2 c = children[p];
-    volatile float4* vlo = nlo;
-    volatile float4* vhi = nhi;
-    float ax = vlo[c.x].x, ay = vlo[c.x].y, az = vlo[c.x].z, bx = vlo[c.y].x, by = vlo[c.y].y, bz = vlo[c.y].z;
-    float Ax = vhi[c.x].x, Ay = vhi[c.x].y, Az = vhi[c.x].z, Bx = vhi[c.y].x, By = vhi[c.y].y, Bz = vhi[c.y].z;
-    nlo[p] = make_float4(fminf(ax, bx), fminf(ay, by), fminf(az, bz), 0.f);
-    nhi[p] = make_float4(fmaxf(Ax, Bx), fmaxf(Ay, By), fmaxf(Az, Bz), 0.f);
-    __threadfence();
-    p = parent[p];
-  }
-}
-
-// ---- 6. emit traversal nodes ---------------------------------------------------------------
-__global__ void k_emit_nodes(int n, const int2* __restrict__ children, const float4* __restrict__ nlo,
-                             const float4* __restrict__ nhi, BvhNode* __restrict__ nodes, int node_base,
-                             int leaf_base) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n - 1) return;
-  int2 c = children[i];
-  float4 l0 = nlo[c.x], h0 = nhi[c.x], l1 = nlo[c.y], h1 = nhi[c.y];
-  BvhNode nd;
-  nd.c0xy = make_float4(l0.x, h0.x, l0.y, h0.y);
-  nd.c1xy = make_float4(l1.x, h1.x, l1.y, h1.y);
-  nd.cz = make_float4(l0.z, h0.z, l1.z, h1.z);
-  bool leaf0 = c.x >= n - 1, leaf1 = c.y >= n - 1;
-  nd.link.x = leaf0 ? ~((leaf_base + (c.x - (n - 1))) << 3) : node_base + c.x;
-  nd.link.y = leaf1 ? ~((leaf_base + (c.y - (n - 1))) << 3) : node_base + c.y;
-  nd.link.z = leaf0 ? 1 : 0;
-  nd.link.w = leaf1 ? 1 : 0;
-  nodes[node_base + i] = nd;
-}
-
-// A BVH over a single primitive: one node whose second child is an empty (inverted) box.
-__global__ void k_emit_single(const float4* __restrict__ blo, const float4* __restrict__ bhi,
-                              BvhNode* __restrict__ nodes, int node_base, int leaf_base, uint32_t* order) {
-  float4 l = blo[0], h = bhi[0];
-  BvhNode nd;
-  nd.c0xy = make_float4(l.x, h.x, l.y, h.y);
-  nd.c1xy = make_float4(FLT_MAX, -FLT_MAX, FLT_MAX, -FLT_MAX);
-  nd.cz = make_float4(l.z, h.z, FLT_MAX, -FLT_MAX);
-  nd.link = make_int4(~(leaf_base << 3), ~(leaf_base << 3), 1, 0);
-  nodes[node_base] = nd;
-  order[0] = 0;
-}
-
-__global__ void k_emit_tris(const AsunaVertex* __restrict__ v, const uint32_t* __restrict__ idx,
-                            const uint32_t* __restrict__ order, uint32_t n, TriSlot* __restrict__ tris) {
-  uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= n) return;
-  uint32_t prim = order[j];
-  const float* p0 = v[idx[3 * prim + 0]].pos;
-  const float* p1 = v[idx[3 * prim + 1]].pos;
-  const float* p2 = v[idx[3 * prim + 2]].pos;
-  TriSlot t;
-  t.v0 = make_float4(p0[0], p0[1], p0[2], __uint_as_float(prim));
-  t.v1 = make_float4(p1[0], p1[1], p1[2], 0.f);
-  t.v2 = make_float4(p2[0], p2[1], p2[2], 0.f);
-  tris[j] = t;
-}
-
-__global__ void k_root_box(int n, const float4* __restrict__ nlo, const float4* __restrict__ nhi,
-                           float4* out_lo, float4* out_hi) {
-  // root is inner node 0 for n >= 2, the single leaf (index 0) for n == 1
-  *out_lo = nlo[0];
-  *out_hi = nhi[0];
-}
-
-// ---- statistics: SAH cost and depth of an emitted BVH (single-thread-per-node walk up is avoided;
-// cost is summed per node from child boxes) ------------------------------------------------------
 __device__ __forceinline__ float half_area(float lx, float hx, float ly, float hy, float lz, float hz) {
   float ex = hx - lx, ey = hy - ly, ez = hz - lz;
   return ex * ey + ey * ez + ez * ex;
 }
-__global__ void k_sah_cost(const BvhNode* __restrict__ nodes, int node_base, int n_nodes, double* cost_sum) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  double c = 0.0;
-  if (i < n_nodes) {
-    BvhNode nd = nodes[node_base + i];
-    float a0 = half_area(nd.c0xy.x, nd.c0xy.y, nd.c0xy.z, nd.c0xy.w, nd.cz.x, nd.cz.y);
-    float a1 = half_area(nd.c1xy.x, nd.c1xy.y, nd.c1xy.z, nd.c1xy.w, nd.cz.z, nd.cz.w);
-    // inner child: traversal step cost 1; leaf child: intersection cost 1 per primitive
-    if (nd.c0xy.x <= nd.c0xy.y) c += (double)a0 * (nd.link.x >= 0 ? 1.0 : (double)nd.link.z);
-    if (nd.c1xy.x <= nd.c1xy.y) c += (double)a1 * (nd.link.y >= 0 ? 1.0 : (double)nd.link.w);
+__device__ __forceinline__ float union_half_area(float4 alo, float4 ahi, float4 blo, float4 bhi) {
+  return half_area(fminf(alo.x, blo.x), fmaxf(ahi.x, bhi.x), fminf(alo.y, blo.y), fmaxf(ahi.y, bhi.y),
+                   fminf(alo.z, blo.z), fmaxf(ahi.z, bhi.z));
+}
+
+// Table of Ylitie et al. 2017 section 4.1 for the merged node `idx` = (l, r):
+//   C(n,1) = min( leaf: A P c_prim  if P <= 3 ,  inner: A c_node + min_k C(l,k) + C(r,8-k) )
+//   C(n,i) = min( min_k C(l,k) + C(r,i-k) , C(n,i-1) )          i = 2..7
+// dec: bit 0 = "C(n,1) is a leaf"; 6 bits per i = 2..8 at 4 + 6 (i-2): (k_left, k_right), 0 = the node itself.
+__device__ void dp_merge(const PlocParams& a, int idx, int l, int r, float area, uint32_t count) {
+  float cl[7], cr[7], c[7];
+#pragma unroll
+  for (int i = 0; i < 7; i++) cl[i] = a.cost[(size_t)l * 7 + i], cr[i] = a.cost[(size_t)r * 7 + i];
+  float best8 = FLT_MAX;
+  uint32_t k8 = 1;
+#pragma unroll
+  for (int k = 1; k <= 7; k++) {
+    float v = cl[k - 1] + cr[7 - k];
+    if (v < best8) best8 = v, k8 = k;
   }
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
-  if ((threadIdx.x & 31) == 0 && c != 0.0) atomicAdd(cost_sum, c);
+  float c_inner = best8 + area * a.cost_node;
+  float c_leaf = count <= (uint32_t)kMaxLeafPrims ? area * (float)count * a.cost_prim : FLT_MAX;
+  uint64_t dec = c_leaf <= c_inner ? kDecLeaf : 0ull;
+  c[0] = fminf(c_leaf, c_inner);
+  dec |= (uint64_t)(k8 | ((8 - k8) << 3)) << (4 + 6 * 6);
+  uint32_t prev = 0;
+#pragma unroll
+  for (int i = 2; i <= 7; i++) {
+    float best = FLT_MAX;
+    uint32_t kb = 1;
+    for (int k = 1; k < i; k++) {
+      float v = cl[k - 1] + cr[i - k - 1];
+      if (v < best) best = v, kb = k;
+    }
+    if (best < c[i - 2]) c[i - 1] = best, prev = kb | ((i - kb) << 3);
+    else c[i - 1] = c[i - 2];
+    dec |= (uint64_t)prev << (4 + 6 * (i - 2));
+  }
+#pragma unroll
+  for (int i = 0; i < 7; i++) a.cost[(size_t)idx * 7 + i] = c[i];
+  a.dec[idx] = dec;
+}
+
+// exclusive scan of one packed counter pair (two 16-bit fields) over a 256-thread block
+__device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t& total, uint32_t* warp_sums) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t s = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
+    if (lane >= o) s += t;
+  }
+  __syncthreads();  // previous use of warp_sums is over
+  if (lane == 31) warp_sums[warp] = s;
+  __syncthreads();
+  uint32_t before = 0, tot = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; w++) {
+    uint32_t x = warp_sums[w];
+    if (w < warp) before += x;
+    tot += x;
+  }
+  total = tot;
+  return before + s - v;
+}
+
+__global__ void __launch_bounds__(kThreads) k_ploc(const PlocParams a) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ uint32_t warp_sums[kThreads / 32];
+  __shared__ uint32_t red[4];
+  const int n = a.n;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  for (uint32_t j = gtid; j < (uint32_t)n; j += gsize) {
+    uint32_t prim = a.order[j];
+    float4 lo = a.blo[prim], hi = a.bhi[prim];
+    lo.w = __uint_as_float(1u);
+    hi.w = 0.f;
+    int node = n - 1 + (int)j;
+    a.nlo[node] = lo;
+    a.nhi[node] = hi;
+    float c = half_area(lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) * a.cost_prim;
+#pragma unroll
+    for (int i = 0; i < 7; i++) a.cost[(size_t)node * 7 + i] = c;
+    a.dec[node] = kDecLeaf;
+    a.cid[0][j] = node;
+    a.clo[0][j] = lo;
+    a.chi[0][j] = hi;
+  }
+  grid.sync();
+  int m = n, cur = 0, next_inner = n - 2;
+  while (m > 1) {
+    const int* cid = a.cid[cur];
+    const float4* clo = a.clo[cur];
+    const float4* chi = a.chi[cur];
+    // phase 1: nearest neighbour inside the radius (ties -> lowest index, so a mutual pair always exists)
+    for (uint32_t i = gtid; i < (uint32_t)m; i += gsize) {
+      float4 lo = clo[i], hi = chi[i];
+      int j0 = max(0, (int)i - kPlocRadius), j1 = min(m - 1, (int)i + kPlocRadius);
+      float best = FLT_MAX;
+      int bj = (int)i == j0 ? j0 + 1 : j0;
+      for (int j = j0; j <= j1; j++) {
+        if (j == (int)i) continue;
+        float d = union_half_area(lo, hi, clo[j], chi[j]);
+        if (d < best) best = d, bj = j;
+      }
+      a.nn[i] = bj;
+    }
+    grid.sync();
+    // phase 2: survivor / merge flags, prefix inside this block's contiguous chunk (keeps Morton order)
+    const int chunk = (m + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int c0 = min(m, (int)blockIdx.x * chunk), c1 = min(m, c0 + chunk);
+    uint32_t run_valid = 0, run_lead = 0;
+    for (int base = c0; base < c1; base += kThreads) {
+      int i = base + (int)threadIdx.x;
+      uint32_t packed = 0;
+      if (i < c1) {
+        int j = a.nn[i];
+        bool mutual = a.nn[j] == i;
+        packed = ((!mutual || i < j) ? 1u : 0u) | ((mutual && i < j) ? 0x10000u : 0u);
+      }
+      uint32_t total;
+      uint32_t excl = block_scan_excl(packed, total, warp_sums);
+      if (i < c1) a.pre[i] = make_uint2(run_valid + (excl & 0xFFFFu), run_lead + (excl >> 16));
+      run_valid += total & 0xFFFFu;
+      run_lead += total >> 16;
+    }
+    if (threadIdx.x == 0) a.block_sums[blockIdx.x] = make_uint2(run_valid, run_lead);
+    grid.sync();
+    // phase 3: global offsets from the block sums, then merge / copy into the next cluster array
+    {
+      uint32_t bv = 0, bl = 0, tv = 0, tl = 0;
+      for (uint32_t b = threadIdx.x; b < gridDim.x; b += kThreads) {
+        uint2 s = a.block_sums[b];
+        tv += s.x, tl += s.y;
+        if (b < blockIdx.x) bv += s.x, bl += s.y;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        bv += __shfl_xor_sync(0xFFFFFFFFu, bv, o);
+        bl += __shfl_xor_sync(0xFFFFFFFFu, bl, o);
+        tv += __shfl_xor_sync(0xFFFFFFFFu, tv, o);
+        tl += __shfl_xor_sync(0xFFFFFFFFu, tl, o);
+      }
+      __syncthreads();
+      if (threadIdx.x < 4) red[threadIdx.x] = 0;
+      __syncthreads();
+      if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&red[0], bv);
+        atomicAdd(&red[1], bl);
+        atomicAdd(&red[2], tv);
+        atomicAdd(&red[3], tl);
+      }
+      __syncthreads();
+    }
+    const uint32_t base_valid = red[0], base_lead = red[1], tot_valid = red[2], tot_lead = red[3];
+    int* ocid = a.cid[cur ^ 1];
+    float4* oclo = a.clo[cur ^ 1];
+    float4* ochi = a.chi[cur ^ 1];
+    for (int i = c0 + (int)threadIdx.x; i < c1; i += kThreads) {
+      int j = a.nn[i];
+      bool mutual = a.nn[j] == i;
+      if (mutual && i > j) continue;
+      uint2 p = a.pre[i];
+      uint32_t pos = base_valid + p.x;
+      float4 lo = clo[i], hi = chi[i];
+      int id = cid[i];
+      if (mutual) {
+        float4 lo2 = clo[j], hi2 = chi[j];
+        int id2 = cid[j];
+        uint32_t count = __float_as_uint(lo.w) + __float_as_uint(lo2.w);
+        lo = make_float4(fminf(lo.x, lo2.x), fminf(lo.y, lo2.y), fminf(lo.z, lo2.z), __uint_as_float(count));
+        hi = make_float4(fmaxf(hi.x, hi2.x), fmaxf(hi.y, hi2.y), fmaxf(hi.z, hi2.z), 0.f);
+        int idx = next_inner - (int)(base_lead + p.y);
+        a.children[idx] = make_int2(id, id2);
+        a.nlo[idx] = lo;
+        a.nhi[idx] = hi;
+        dp_merge(a, idx, id, id2, half_area(lo.x, hi.x, lo.y, hi.y, lo.z, hi.z), count);
+        id = idx;
+      }
+      ocid[pos] = id;
+      oclo[pos] = lo;
+      ochi[pos] = hi;
+    }
+    grid.sync();
+    m = (int)tot_valid;
+    next_inner -= (int)tot_lead;
+    cur ^= 1;
+  }
+}
+
+// ---- 5. collapse into compressed 8-wide nodes, level by level ---------------------------------
+struct EmitParams {
+  int n;
+  const int2* children;
+  const float4* nlo;
+  const float4* nhi;
+  const uint64_t* dec;
+  const float* cost;
+  const uint32_t* order;   // sorted position -> primitive id
+  WideNode* nodes;         // absolute array
+  uint32_t node_base;      // this BVH's first wide node (its root)
+  uint32_t prim_base;      // this BVH's first primitive slot
+  int* root_of;            // [n] binary subtree root of wide node (node_base + i)
+  uint32_t* counters;      // [0] wide nodes handed out, [1] primitive slots handed out
+  // primitive payload: triangles of a mesh, or instance ids of the top level
+  const AsunaVertex* v;
+  const uint32_t* idx;
+  TriSlot* tris;
+  uint32_t* leaf_inst;
+  // results for the host / the top-level build
+  float4* out_lo;
+  float4* out_hi;
+  BuildResult* result;
+};
+
+__device__ __forceinline__ uint32_t pack4(const uint8_t* b) {
+  return (uint32_t)b[0] | ((uint32_t)b[1] << 8) | ((uint32_t)b[2] << 16) | ((uint32_t)b[3] << 24);
+}
+
+__device__ void emit_prim(const EmitParams& a, uint32_t slot, uint32_t prim) {
+  if (a.tris) {
+    const float* p0 = a.v[a.idx[3 * (size_t)prim + 0]].pos;
+    const float* p1 = a.v[a.idx[3 * (size_t)prim + 1]].pos;
+    const float* p2 = a.v[a.idx[3 * (size_t)prim + 2]].pos;
+    TriSlot t;
+    t.v0 = make_float4(p0[0], p0[1], p0[2], __uint_as_float(prim));
+    t.v1 = make_float4(p1[0], p1[1], p1[2], 0.f);
+    t.v2 = make_float4(p2[0], p2[1], p2[2], 0.f);
+    a.tris[slot] = t;
+  } else {
+    a.leaf_inst[slot] = prim;
+  }
+}
+
+__device__ void emit_wide_node(const EmitParams& a, uint32_t w) {
+  const int n = a.n;
+  const int root = a.root_of[w];
+  int ch_node[8];
+  bool ch_leaf[8];
+  int nc = 0;
+  {
+    uint64_t droot = a.dec[root];
+    if (root >= n - 1 || (droot & kDecLeaf)) {
+      ch_node[0] = root, ch_leaf[0] = true, nc = 1;  // a BVH of <= 3 primitives: one leaf child
+    } else {
+      int st_node[8], st_bud[8], sp = 0;
+      int2 c = a.children[root];
+      uint32_t k = (uint32_t)(droot >> (4 + 6 * 6)) & 63u;
+      st_node[sp] = c.y, st_bud[sp++] = (int)(k >> 3);
+      st_node[sp] = c.x, st_bud[sp++] = (int)(k & 7u);
+      while (sp > 0) {
+        int x = st_node[--sp], bud = st_bud[sp];
+        bool leaf2 = x >= n - 1;
+        uint64_t d = a.dec[x];
+        uint32_t code = (bud >= 2 && !leaf2) ? (uint32_t)(d >> (4 + 6 * (bud - 2))) & 63u : 0u;
+        if (code == 0u) {
+          ch_node[nc] = x, ch_leaf[nc] = leaf2 || (d & kDecLeaf), nc++;
+        } else {
+          int2 cc = a.children[x];
+          st_node[sp] = cc.y, st_bud[sp++] = (int)(code >> 3);
+          st_node[sp] = cc.x, st_bud[sp++] = (int)(code & 7u);
+        }
+      }
+    }
+  }
+  float4 rlo = a.nlo[root], rhi = a.nhi[root];
+  float4 clo[8], chi[8];
+  for (int i = 0; i < nc; i++) clo[i] = a.nlo[ch_node[i]], chi[i] = a.nhi[ch_node[i]];
+
+  // octant-ordered slots: greedy assignment maximising sum dot(child centre - node centre, dir(slot)),
+  // dir(slot) = +1 on the axes whose slot bit is set (x = bit 0), so slot ^ ray-octant is front to back
+  int slot_of[8];
+  {
+    float cx = 0.5f * (rlo.x + rhi.x), cy = 0.5f * (rlo.y + rhi.y), cz = 0.5f * (rlo.z + rhi.z);
+    float dx[8], dy[8], dz[8];
+    for (int i = 0; i < nc; i++) {
+      dx[i] = 0.5f * (clo[i].x + chi[i].x) - cx, dy[i] = 0.5f * (clo[i].y + chi[i].y) - cy;
+      dz[i] = 0.5f * (clo[i].z + chi[i].z) - cz;
+      slot_of[i] = -1;
+    }
+    uint32_t slot_used = 0;
+    for (int round = 0; round < nc; round++) {
+      float best = -FLT_MAX;
+      int bi = 0, bs = 0;
+      for (int i = 0; i < nc; i++) {
+        if (slot_of[i] >= 0) continue;
+        for (int s = 0; s < 8; s++) {
+          if (slot_used & (1u << s)) continue;
+          float v = ((s & 1) ? dx[i] : -dx[i]) + ((s & 2) ? dy[i] : -dy[i]) + ((s & 4) ? dz[i] : -dz[i]);
+          if (v > best) best = v, bi = i, bs = s;
+        }
+      }
+      slot_of[bi] = bs;
+      slot_used |= 1u << bs;
+    }
+  }
+  int child_in_slot[8];
+  for (int s = 0; s < 8; s++) child_in_slot[s] = -1;
+  uint32_t n_inner = 0, n_prims = 0;
+  for (int i = 0; i < nc; i++) {
+    child_in_slot[slot_of[i]] = i;
+    if (ch_leaf[i]) n_prims += __float_as_uint(clo[i].w);
+    else n_inner++;
+  }
+  uint32_t cb = n_inner ? atomicAdd(&a.counters[0], n_inner) : 0u;
+  uint32_t pb = n_prims ? atomicAdd(&a.counters[1], n_prims) : 0u;
+
+  // quantisation grid: origin = padded lower corner, per-axis power-of-two scale covering the padded extent
+  float pad[3], p[3], inv_scale[3];
+  uint8_t e[3];
+  {
+    const float lo3[3] = {rlo.x, rlo.y, rlo.z}, hi3[3] = {rhi.x, rhi.y, rhi.z};
+    for (int k = 0; k < 3; k++) {
+      pad[k] = fmaxf(fabsf(lo3[k]), fabsf(hi3[k])) * 2.4e-7f + 1e-30f;
+      p[k] = lo3[k] - pad[k];
+      float f = ((hi3[k] + pad[k]) - p[k]) * (1.0f / 254.0f);
+      uint32_t bits = __float_as_uint(f);
+      uint32_t eb = (bits >> 23) + ((bits & 0x7FFFFFu) ? 1u : 0u);
+      eb = min(max(eb, 1u), 253u);
+      e[k] = (uint8_t)eb;
+      inv_scale[k] = __uint_as_float((254u - eb) << 23);
+    }
+  }
+  WideNode nd;
+  nd.px = p[0], nd.py = p[1], nd.pz = p[2];
+  nd.ex = e[0], nd.ey = e[1], nd.ez = e[2];
+  nd.child_base = a.node_base + cb;
+  nd.prim_base = a.prim_base + pb;
+  uint32_t imask = 0, inner_rank = 0, prim_off = 0;
+  for (int s = 0; s < 8; s++) {
+    int i = child_in_slot[s];
+    if (i < 0) {
+      nd.meta[s] = 0;
+      nd.qlox[s] = nd.qloy[s] = nd.qloz[s] = 255;
+      nd.qhix[s] = nd.qhiy[s] = nd.qhiz[s] = 0;
+      continue;
+    }
+    const float lo3[3] = {clo[i].x, clo[i].y, clo[i].z}, hi3[3] = {chi[i].x, chi[i].y, chi[i].z};
+    uint8_t ql[3], qh[3];
+    for (int k = 0; k < 3; k++) {
+      float fl = floorf((lo3[k] - pad[k] - p[k]) * inv_scale[k]);
+      float fh = ceilf((hi3[k] + pad[k] - p[k]) * inv_scale[k]);
+      ql[k] = (uint8_t)fminf(fmaxf(fl, 0.f), 255.f);
+      qh[k] = (uint8_t)fminf(fmaxf(fh, 0.f), 255.f);
+    }
+    nd.qlox[s] = ql[0], nd.qloy[s] = ql[1], nd.qloz[s] = ql[2];
+    nd.qhix[s] = qh[0], nd.qhiy[s] = qh[1], nd.qhiz[s] = qh[2];
+    if (!ch_leaf[i]) {
+      imask |= 1u << s;
+      nd.meta[s] = (uint8_t)(0x20u | (24u + (uint32_t)s));
+      a.root_of[cb + inner_rank] = ch_node[i];
+      inner_rank++;
+    } else {
+      uint32_t cnt = __float_as_uint(clo[i].w);
+      nd.meta[s] = (uint8_t)((((1u << cnt) - 1u) << 5) | prim_off);
+      // the <= 3 primitives of the subtree, in sorted order
+      int st[4], sp = 0;
+      st[sp++] = ch_node[i];
+      uint32_t k = 0;
+      while (sp > 0) {
+        int x = st[--sp];
+        if (x >= n - 1) {
+          emit_prim(a, a.prim_base + pb + prim_off + k, a.order[x - (n - 1)]);
+          k++;
+        } else {
+          int2 cc = a.children[x];
+          st[sp++] = cc.y;
+          st[sp++] = cc.x;
+        }
+      }
+      prim_off += cnt;
+    }
+  }
+  nd.imask = (uint8_t)imask;
+  // five 16-byte stores
+  uint4* out = reinterpret_cast<uint4*>(a.nodes + a.node_base + w);
+  const uint8_t eb[4] = {nd.ex, nd.ey, nd.ez, nd.imask};
+  out[0] = make_uint4(__float_as_uint(nd.px), __float_as_uint(nd.py), __float_as_uint(nd.pz), pack4(eb));
+  out[1] = make_uint4(nd.child_base, nd.prim_base, pack4(nd.meta), pack4(nd.meta + 4));
+  out[2] = make_uint4(pack4(nd.qlox), pack4(nd.qlox + 4), pack4(nd.qloy), pack4(nd.qloy + 4));
+  out[3] = make_uint4(pack4(nd.qloz), pack4(nd.qloz + 4), pack4(nd.qhix), pack4(nd.qhix + 4));
+  out[4] = make_uint4(pack4(nd.qhiy), pack4(nd.qhiy + 4), pack4(nd.qhiz), pack4(nd.qhiz + 4));
+}
+
+__global__ void __launch_bounds__(kThreads) k_emit_wide(const EmitParams a) {
+  cg::grid_group grid = cg::this_grid();
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
+  if (gtid == 0) {
+    a.root_of[0] = 0;  // binary root (for n == 1 the single leaf is node n-1 = 0 as well)
+    a.counters[0] = 1;
+    a.counters[1] = 0;
+  }
+  grid.sync();
+  uint32_t begin = 0, end = 1;
+  while (begin < end) {
+    for (uint32_t w = begin + gtid; w < end; w += gsize) emit_wide_node(a, w);
+    grid.sync();
+    begin = end;
+    end = *(volatile uint32_t*)&a.counters[0];
+    grid.sync();  // everyone has read the level boundary before the next level allocates
+  }
+  if (gtid == 0) {
+    float4 lo = a.nlo[0], hi = a.nhi[0];
+    if (a.out_lo) *a.out_lo = lo, *a.out_hi = hi;
+    if (a.result) {
+      float area = half_area(lo.x, hi.x, lo.y, hi.y, lo.z, hi.z);
+      a.result->wide_nodes = end;
+      a.result->prim_slots = a.counters[1];
+      a.result->sah_cost = area > 0.f ? a.cost[0] / area : 0.f;
+      a.result->pad = 0;
+    }
+  }
 }
 
 inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -385,23 +695,36 @@ inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 // ------------------------------------------------------------------------------------------------
 BuildScratch::~BuildScratch() { release(); }
 void BuildScratch::release() {
-  void* ptrs[] = {blo, bhi, keys[0], keys[1], vals[0], vals[1], hist, children, parent, nlo, nhi, flags, bounds};
+  void* ptrs[] = {blo, bhi, keys[0], keys[1], vals[0], vals[1], hist, children, nlo, nhi, cost, dec, cid[0], cid[1],
+                  clo[0], clo[1], chi[0], chi[1], nn, pre, block_sums, root_of, counters, bounds};
   for (void* p : ptrs)
     if (p) cudaFree(p);
   blo = bhi = nlo = nhi = nullptr;
   keys[0] = keys[1] = nullptr;
   vals[0] = vals[1] = nullptr;
-  hist = flags = nullptr;
+  hist = counters = nullptr;
   children = nullptr;
-  parent = nullptr;
+  cost = nullptr;
+  dec = nullptr;
+  cid[0] = cid[1] = nn = root_of = nullptr;
+  clo[0] = clo[1] = chi[0] = chi[1] = nullptr;
+  pre = block_sums = nullptr;
   bounds = nullptr;
   capacity = 0;
 }
 cudaError_t BuildScratch::reserve(uint32_t n) {
+  cudaError_t e;
+  if (coop_blocks == 0) {
+    int dev = 0, sms = 0, per_sm_a = 0, per_sm_b = 0;
+    if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
+    if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_ploc, kThreads, 0)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_emit_wide, kThreads, 0)) != cudaSuccess) return e;
+    coop_blocks = (uint32_t)(sms * std::max(1, std::min(std::min(per_sm_a, per_sm_b), 4)));
+  }
   if (n <= capacity) return cudaSuccess;
   release();
   uint32_t cap = std::max<uint32_t>(n, 1024);
-  cudaError_t e;
 #define A(ptr, bytes)                                   \
   if ((e = cudaMalloc((void**)&ptr, (bytes))) != cudaSuccess) return e;
   A(blo, sizeof(float4) * cap);
@@ -412,10 +735,20 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
   A(vals[1], sizeof(uint32_t) * cap);
   A(hist, sizeof(uint32_t) * 256 * (size_t)div_up(cap, kSortTile));
   A(children, sizeof(int2) * cap);
-  A(parent, sizeof(int) * 2 * (size_t)cap);
   A(nlo, sizeof(float4) * 2 * (size_t)cap);
   A(nhi, sizeof(float4) * 2 * (size_t)cap);
-  A(flags, sizeof(uint32_t) * cap);
+  A(cost, sizeof(float) * 7 * 2 * (size_t)cap);
+  A(dec, sizeof(uint64_t) * 2 * (size_t)cap);
+  for (int k = 0; k < 2; k++) {
+    A(cid[k], sizeof(int) * cap);
+    A(clo[k], sizeof(float4) * cap);
+    A(chi[k], sizeof(float4) * cap);
+  }
+  A(nn, sizeof(int) * cap);
+  A(pre, sizeof(uint2) * cap);
+  A(block_sums, sizeof(uint2) * 4096);
+  A(root_of, sizeof(int) * cap);
+  A(counters, sizeof(uint32_t) * 4);
   A(bounds, sizeof(int) * 8);
 #undef A
   capacity = cap;
@@ -433,17 +766,7 @@ void launch_instance_boxes(cudaStream_t s, const DInstance* inst, const float4* 
   k_instance_boxes<<<div_up(n, kThreads), kThreads, 0, s>>>(inst, mesh_lo, mesh_hi, n, sc.blo, sc.bhi, sc.bounds);
 }
 
-// Builds the BVH over the n boxes already in sc.blo/bhi (bounds in sc.bounds).  On return (stream
-// order) nodes[node_base .. node_base+max(n-1,1)) are written and sc.vals[0] holds the leaf order.
-void launch_lbvh(cudaStream_t s, uint32_t n, BvhNode* nodes, int node_base, int leaf_base, BuildScratch& sc,
-                 float4* root_lo, float4* root_hi) {
-  if (n == 1) {
-    k_emit_single<<<1, 1, 0, s>>>(sc.blo, sc.bhi, nodes, node_base, leaf_base, sc.vals[0]);
-    if (root_lo) k_root_box<<<1, 1, 0, s>>>(1, sc.blo, sc.bhi, root_lo, root_hi);
-    return;
-  }
-  uint32_t nb = div_up(n, kThreads);
-  k_morton<<<nb, kThreads, 0, s>>>(sc.blo, sc.bhi, n, sc.bounds, sc.keys[0], sc.vals[0]);
+static void sort_passes(cudaStream_t s, uint32_t n, BuildScratch& sc) {
   uint32_t sort_blocks = div_up(n, kSortTile);
   int cur = 0;
   for (int shift = 0; shift < 64; shift += 8) {
@@ -453,23 +776,42 @@ void launch_lbvh(cudaStream_t s, uint32_t n, BvhNode* nodes, int node_base, int 
                                                     n, shift, sc.hist, sort_blocks);
     cur ^= 1;
   }
-  // 8 passes: result is back in buffer 0
-  k_lbvh_hierarchy<<<div_up(n - 1, kThreads), kThreads, 0, s>>>(sc.keys[0], (int)n, sc.children, sc.parent);
-  cudaMemsetAsync(sc.flags, 0, sizeof(uint32_t) * n, s);
-  k_lbvh_fit<<<nb, kThreads, 0, s>>>(sc.blo, sc.bhi, sc.vals[0], (int)n, sc.children, sc.parent, sc.nlo, sc.nhi,
-                                      sc.flags);
-  k_emit_nodes<<<div_up(n - 1, kThreads), kThreads, 0, s>>>((int)n, sc.children, sc.nlo, sc.nhi, nodes, node_base,
-                                                            leaf_base);
-  if (root_lo) k_root_box<<<1, 1, 0, s>>>((int)n, sc.nlo, sc.nhi, root_lo, root_hi);
+  // 8 passes: the result is back in buffer 0
 }
 
-void launch_emit_tris(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, const uint32_t* order,
-                      TriSlot* tris) {
-  k_emit_tris<<<div_up(n, kThreads), kThreads, 0, s>>>(v, idx, order, n, tris);
-}
-
-void launch_sah_cost(cudaStream_t s, const BvhNode* nodes, int node_base, int n_nodes, double* cost_sum) {
-  k_sah_cost<<<div_up((uint32_t)n_nodes, kThreads), kThreads, 0, s>>>(nodes, node_base, n_nodes, cost_sum);
+// Builds the wide BVH over the n boxes already in sc.blo/bhi (bounds in sc.bounds): nodes[node_base ..) receive the
+// wide nodes (root first), primitive slots prim_base.. are filled through `payload` (triangles or instance ids).
+cudaError_t launch_build_wide(cudaStream_t s, uint32_t n, WideNode* nodes, uint32_t node_base, uint32_t prim_base,
+                              BuildScratch& sc, const PrimPayload& payload, float cost_prim, float4* root_lo,
+                              float4* root_hi, BuildResult* result) {
+  if (n >= 2) {
+    k_morton<<<div_up(n, kThreads), kThreads, 0, s>>>(sc.blo, sc.bhi, n, sc.bounds, sc.keys[0], sc.vals[0]);
+    sort_passes(s, n, sc);
+  } else {
+    cudaMemsetAsync(sc.vals[0], 0, sizeof(uint32_t), s);
+  }
+  uint32_t grid = std::max(1u, std::min(sc.coop_blocks, div_up(n, kThreads)));
+  PlocParams pp;
+  pp.n = (int)n;
+  pp.cost_node = 1.0f;
+  pp.cost_prim = cost_prim;
+  pp.blo = sc.blo, pp.bhi = sc.bhi, pp.order = sc.vals[0];
+  pp.nlo = sc.nlo, pp.nhi = sc.nhi, pp.children = sc.children, pp.cost = sc.cost, pp.dec = sc.dec;
+  for (int k = 0; k < 2; k++) pp.cid[k] = sc.cid[k], pp.clo[k] = sc.clo[k], pp.chi[k] = sc.chi[k];
+  pp.nn = sc.nn, pp.pre = sc.pre, pp.block_sums = sc.block_sums;
+  void* pargs[] = {&pp};
+  cudaError_t e = cudaLaunchCooperativeKernel((const void*)k_ploc, dim3(grid), dim3(kThreads), pargs, 0, s);
+  if (e != cudaSuccess) return e;
+  EmitParams ep;
+  ep.n = (int)n;
+  ep.children = sc.children, ep.nlo = sc.nlo, ep.nhi = sc.nhi, ep.dec = sc.dec, ep.cost = sc.cost;
+  ep.order = sc.vals[0];
+  ep.nodes = nodes, ep.node_base = node_base, ep.prim_base = prim_base;
+  ep.root_of = sc.root_of, ep.counters = sc.counters;
+  ep.v = payload.vertices, ep.idx = payload.indices, ep.tris = payload.tris, ep.leaf_inst = payload.leaf_inst;
+  ep.out_lo = root_lo, ep.out_hi = root_hi, ep.result = result;
+  void* eargs[] = {&ep};
+  return cudaLaunchCooperativeKernel((const void*)k_emit_wide, dim3(grid), dim3(kThreads), eargs, 0, s);
 }
 
 // Host-side debug/test hook: sorts (key,value) pairs with the builder's radix sort.
@@ -478,15 +820,7 @@ cudaError_t radix_sort_pairs(cudaStream_t s, uint64_t* keys_io, uint32_t* vals_i
   if (e != cudaSuccess) return e;
   cudaMemcpyAsync(sc.keys[0], keys_io, sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, s);
   cudaMemcpyAsync(sc.vals[0], vals_io, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s);
-  uint32_t sort_blocks = div_up(n, kSortTile);
-  int cur = 0;
-  for (int shift = 0; shift < 64; shift += 8) {
-    k_sort_hist<<<sort_blocks, kThreads, 0, s>>>(sc.keys[cur], n, shift, sc.hist, sort_blocks);
-    k_sort_scan<<<1, 1024, 0, s>>>(sc.hist, 256u * sort_blocks);
-    k_sort_scatter<<<sort_blocks, kThreads, 0, s>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1], sc.vals[cur ^ 1],
-                                                    n, shift, sc.hist, sort_blocks);
-    cur ^= 1;
-  }
+  sort_passes(s, n, sc);
   cudaMemcpyAsync(keys_io, sc.keys[0], sizeof(uint64_t) * n, cudaMemcpyDeviceToDevice, s);
   cudaMemcpyAsync(vals_io, sc.vals[0], sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, s);
   return cudaGetLastError();

@@ -17,17 +17,29 @@
 namespace asuna {
 
 // ---- acceleration structure -------------------------------------------------------------
-// Binary BVH node in the Aila-Laine layout: the node carries the boxes of its two children so
-// one 64-byte fetch (4 x LDG.128) decides both.  link >= 0: absolute index of an inner node;
-// link < 0: ~link = (first leaf slot << 3) | (slot count - 1), 1..8 consecutive slots
-// (0x80000000 is reserved as the traversal's leave-instance sentinel, so slots < 2^27).
-struct __align__(16) BvhNode {
-  float4 c0xy;   // child0: lo.x, hi.x, lo.y, hi.y
-  float4 c1xy;   // child1: lo.x, hi.x, lo.y, hi.y
-  float4 cz;     // child0 lo.z, hi.z, child1 lo.z, hi.z
-  int4 link;     // child0, child1, count0, count1
+// Compressed 8-wide BVH node (80 bytes = 5 x LDG.128), after Ylitie, Karras, Laine 2017
+// "Efficient Incoherent Ray Traversal on GPUs Through Compressed Wide BVHs".  The eight child boxes are
+// quantised to 8 bits per plane on a per-node grid: plane = p + q * 2^e (conservative: lo
+// rounded down, hi rounded up, after a 2-ulp pad).  Children sit in octant-ordered slots so that
+// visiting slot (s ^ ray octant) approximates front-to-back order without sorting.
+//   meta[s] = 0                         empty slot
+//   meta[s] = 001 | (24 + s)            inner child; its node index is child_base + popc(imask & below(s))
+//   meta[s] = unary(count) | offset     leaf child: `count` (1..3) consecutive primitive slots from
+//                                       prim_base + offset (offset < 24)
+// The same node type serves both levels: in a mesh BVH (BLAS) primitive slots are TriSlot entries,
+// in the instance BVH (TLAS) they index tlas_leaf_inst.
+struct __align__(16) WideNode {
+  float px, py, pz;      // grid origin
+  uint8_t ex, ey, ez;    // biased exponents: scale = uint_as_float(e << 23)
+  uint8_t imask;         // which slots hold inner children
+  uint32_t child_base;   // absolute index of the first inner child
+  uint32_t prim_base;    // absolute index of the first primitive slot
+  uint8_t meta[8];
+  uint8_t qlox[8], qloy[8], qloz[8];
+  uint8_t qhix[8], qhiy[8], qhiz[8];
 };
-static_assert(sizeof(BvhNode) == 64, "node is one 64-byte line half");
+static_assert(sizeof(WideNode) == 80, "compressed wide node is 80 bytes");
+constexpr int kMaxLeafPrims = 3;
 
 // Triangle slot in BVH-leaf order: three float4 (48 B), prim id in v0.w.
 struct __align__(16) TriSlot {
@@ -39,7 +51,7 @@ struct __align__(16) TriSlot {
 struct __align__(16) DInstance {
   float4 w2o[3];      // world->object rows (3x4)
   float4 o2w[3];      // object->world rows (3x4)
-  int32_t blas_root;  // absolute node index of the mesh BVH root
+  int32_t blas_root;  // absolute wide-node index of the mesh BVH root
   uint32_t mesh;
   uint32_t material;
   int32_t light;      // >= 0: emitter instance
@@ -62,9 +74,9 @@ struct DTexture {
 
 // Everything a render kernel needs, passed by value (fits the 4 KB kernel-parameter space).
 struct SceneView {
-  const BvhNode* tlas_nodes;      // top-level nodes; leaves index tlas_leaf_inst
+  const WideNode* tlas_nodes;     // top-level nodes (root 0); leaf slots index tlas_leaf_inst
   const uint32_t* tlas_leaf_inst;
-  const BvhNode* blas_nodes;      // all mesh BVHs, absolute indices
+  const WideNode* blas_nodes;     // all mesh BVHs, absolute indices
   const TriSlot* tris;            // all mesh triangles in leaf order, absolute indices
   const DInstance* instances;
   const DMesh* meshes;

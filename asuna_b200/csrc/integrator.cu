@@ -23,8 +23,7 @@ namespace {
 
 constexpr int kTraceThreads = 128;
 constexpr int kShadeThreads = 128;
-constexpr int kStackSize = 96;
-constexpr int kSentinel = (int)0x80000000;  // "leave the current instance"
+constexpr int kStackSize = 40;  // uint2 entries: wide-BVH depth of the instance level + one mesh level
 
 struct HitRec {
   float t, b1, b2;
@@ -38,6 +37,7 @@ struct RaySpace {  // ray constants in the space being traversed (world or one i
   int kx, ky, kz;       // watertight test: axis permutation
   float Sx, Sy, Sz;     // and shear
   float3 d;
+  uint32_t octinv4;     // (7 ^ octant) replicated in the four bytes; octant bit k = direction negative on axis k
 };
 
 ADEV void setup_shear(RaySpace& r) {
@@ -59,18 +59,50 @@ ADEV void setup_space(RaySpace& r, float3 o, float3 d) {
   r.o = o;
   r.d = d;
   r.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+  uint32_t oct = (r.idir.x < 0.f ? 1u : 0u) | (r.idir.y < 0.f ? 2u : 0u) | (r.idir.z < 0.f ? 4u : 0u);
+  r.octinv4 = (7u ^ oct) * 0x01010101u;
 }
 
-// slab test; far plane widened by 2 ulp so it never rejects what the watertight triangle test accepts
-ADEV bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, const RaySpace& r, float tmin,
-               float tmax, float& tnear) {
-  float tx0 = (lox - r.o.x) * r.idir.x, tx1 = (hix - r.o.x) * r.idir.x;
-  float ty0 = (loy - r.o.y) * r.idir.y, ty1 = (hiy - r.o.y) * r.idir.y;
-  float tz0 = (loz - r.o.z) * r.idir.z, tz1 = (hiz - r.o.z) * r.idir.z;
-  float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), tmin));
-  float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fminf(fmaxf(tz0, tz1), tmax));
-  tnear = tn;
-  return tn <= tf * 1.0000004f;
+ADEV float byte_f(uint32_t v, int j) { return (float)((v >> (8 * j)) & 0xFFu); }
+
+// Slab test of the eight quantised child boxes of one compressed wide node (Ylitie et al. 2017, section 3):
+// plane t = q * (2^e / d) + (p - o) / d.  Returns the hit mask: inner children set bit 24 + (slot ^ octinv)
+// (so the highest set bit is the nearest octant), leaf children set their primitive bits [offset, offset+count).
+// The far plane is widened by 2 ulp so the box never rejects what the watertight triangle test accepts.
+ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 n4, const RaySpace& r, float tmin,
+                                  float tmax) {
+  const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * r.idir.x;
+  const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * r.idir.y;
+  const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * r.idir.z;
+  const float bx = (__uint_as_float(n0.x) - r.o.x) * r.idir.x;
+  const float by = (__uint_as_float(n0.y) - r.o.y) * r.idir.y;
+  const float bz = (__uint_as_float(n0.z) - r.o.z) * r.idir.z;
+  const bool nx = r.idir.x < 0.f, ny = r.idir.y < 0.f, nz = r.idir.z < 0.f;
+  uint32_t hitmask = 0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const uint32_t meta4 = h ? n1.w : n1.z;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
+    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
+    const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
+    const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
+    const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
+    const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
+    const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
+    const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float tnx = fmaf(byte_f(nearx, j), ax, bx), tfx = fmaf(byte_f(farx, j), ax, bx);
+      float tny = fmaf(byte_f(neary, j), ay, by), tfy = fmaf(byte_f(fary, j), ay, by);
+      float tnz = fmaf(byte_f(nearz, j), az, bz), tfz = fmaf(byte_f(farz, j), az, bz);
+      float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
+      float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
+      if (cmin <= cmax * 1.0000004f)
+        hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
+    }
+  }
+  return hitmask;
 }
 
 // Watertight ray/triangle test, no culling.  Barycentrics in the Vulkan convention.
@@ -104,84 +136,92 @@ ADEV bool hit_triangle(const RaySpace& r, float3 v0, float3 v1, float3 v2, float
 // Two-level traversal with traceRayEXT semantics: per instance the ray is taken into object space
 // (origin and unnormalised direction through world->object), t is shared between spaces.
 // Ties are broken toward the lower (instance, primitive) pair, as the oracle defines.
+// Stack entries are (base index, mask) groups: mask > 0x00FFFFFF = a node group (hit bits of inner
+// children in the top byte, imask in the low byte), otherwise a primitive group (<= 24 hit bits).
 template <bool ANY, bool COUNT = false>
 __device__ bool traverse(const SceneView& sc, float3 wo, float3 wd, float tmin, float tmax, HitRec& best,
                          uint32_t* overflow, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
   if (sc.n_instances == 0) return false;
-  int stack[kStackSize];
-  int sp = 0;
+  uint2 stack[kStackSize];
+  int sp = 0, blas_sp = 0;
   RaySpace rs;
   setup_space(rs, wo, wd);
   bool in_blas = false, found = false;
   uint32_t cur_inst = 0;
-  int cur = 0;  // TLAS root
+  const WideNode* nodes = sc.tlas_nodes;
+  uint2 ng = make_uint2(0u, 0x80000000u), tg = make_uint2(0u, 0u);
   for (;;) {
-    if (cur >= 0) {
-      const BvhNode* np = (in_blas ? sc.blas_nodes : sc.tlas_nodes) + cur;
-      if (COUNT) (*n_nodes)++;
-      float4 a = __ldg(&np->c0xy), b = __ldg(&np->c1xy), z = __ldg(&np->cz);
-      int4 link = __ldg(&np->link);
-      float t0, t1;
-      bool h0 = slab(a.x, a.y, a.z, a.w, z.x, z.y, rs, tmin, tmax, t0);
-      bool h1 = slab(b.x, b.y, b.z, b.w, z.z, z.w, rs, tmin, tmax, t1);
-      if (h0 && h1) {
-        bool swap = t1 < t0;
-        int nearc = swap ? link.y : link.x, farc = swap ? link.x : link.y;
-        if (sp < kStackSize) stack[sp++] = farc;
+    if (ng.y > 0x00FFFFFFu) {
+      const uint32_t hits = ng.y;
+      const uint32_t bit = 31u - (uint32_t)__clz(hits);
+      ng.y &= ~(1u << bit);
+      if (ng.y > 0x00FFFFFFu) {
+        if (sp < kStackSize) stack[sp++] = ng;
         else atomicAdd(overflow, 1u);
-        cur = nearc;
-        continue;
-      } else if (h0) {
-        cur = link.x;
-        continue;
-      } else if (h1) {
-        cur = link.y;
-        continue;
       }
-    } else if (cur != kSentinel) {
-      uint32_t code = ~(uint32_t)cur;
-      uint32_t first = code >> 3, cnt = (code & 7u) + 1u;
-      if (in_blas) {
-        for (uint32_t k = 0; k < cnt; k++) {
-          const TriSlot* tp = sc.tris + first + k;
-          float4 v0 = __ldg(&tp->v0), v1 = __ldg(&tp->v1), v2 = __ldg(&tp->v2);
-          float t, b1, b2;
-          if (COUNT) (*n_tris)++;
-          if (!hit_triangle(rs, f3(v0), f3(v1), f3(v2), t, b1, b2)) continue;
-          if (!(t > tmin)) continue;
-          uint32_t prim = __float_as_uint(v0.w);
-          bool closer = t < tmax || (t == tmax && found &&
-                                     (cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim)));
-          if (!closer) continue;
-          best.t = t, best.b1 = b1, best.b2 = b2, best.inst = cur_inst, best.prim = prim;
-          tmax = t;
-          found = true;
-          if (ANY) return true;
-        }
+      const uint32_t slot = (bit - 24u) ^ (rs.octinv4 & 7u);
+      const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+      const uint4* np = reinterpret_cast<const uint4*>(nodes + ng.x + rel);
+      if (COUNT) (*n_nodes)++;
+      const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+      const uint32_t hm = intersect_wide_node(n0, n1, n2, n3, n4, rs, tmin, tmax);
+      ng = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
+      tg = make_uint2(n1.y, hm & 0x00FFFFFFu);
+    } else {
+      tg = ng;
+      ng = make_uint2(0u, 0u);
+    }
+    if (in_blas) {
+      while (tg.y) {
+        const uint32_t k = (uint32_t)__ffs((int)tg.y) - 1u;
+        tg.y &= tg.y - 1u;
+        const TriSlot* tp = sc.tris + tg.x + k;
+        float4 v0 = __ldg(&tp->v0), v1 = __ldg(&tp->v1), v2 = __ldg(&tp->v2);
+        float t, b1, b2;
+        if (COUNT) (*n_tris)++;
+        if (!hit_triangle(rs, f3(v0), f3(v1), f3(v2), t, b1, b2)) continue;
+        if (!(t > tmin)) continue;
+        uint32_t prim = __float_as_uint(v0.w);
+        bool closer = t < tmax || (t == tmax && found &&
+                                   (cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim)));
+        if (!closer) continue;
+        best.t = t, best.b1 = b1, best.b2 = b2, best.inst = cur_inst, best.prim = prim;
+        tmax = t;
+        found = true;
+        if (ANY) return true;
+      }
+    } else if (tg.y) {
+      // instance group: enter the first instance, keep the rest (and the pending node group) for later
+      const uint32_t k = (uint32_t)__ffs((int)tg.y) - 1u;
+      tg.y &= tg.y - 1u;
+      if (sp + 2 > kStackSize) {
+        atomicAdd(overflow, 1u);
       } else {
-        // TLAS leaf: enter the first instance, keep the rest of the leaf for later
-        if (cnt > 1) {
-          if (sp < kStackSize) stack[sp++] = (int)~(((first + 1) << 3) | (cnt - 2));
-          else atomicAdd(overflow, 1u);
-        }
-        cur_inst = __ldg(&sc.tlas_leaf_inst[first]);
+        if (tg.y) stack[sp++] = tg;
+        if (ng.y > 0x00FFFFFFu) stack[sp++] = ng;
+        cur_inst = __ldg(&sc.tlas_leaf_inst[tg.x + k]);
         const DInstance* in = sc.instances + cur_inst;
         float4 r0 = __ldg(&in->w2o[0]), r1 = __ldg(&in->w2o[1]), r2 = __ldg(&in->w2o[2]);
         float4 m[3] = {r0, r1, r2};
         setup_space(rs, xf_point(m, wo), xf_vector(m, wd));
         setup_shear(rs);
-        if (sp < kStackSize) stack[sp++] = kSentinel;
-        else atomicAdd(overflow, 1u);
         in_blas = true;
-        cur = __ldg(&in->blas_root);
+        blas_sp = sp;
+        nodes = sc.blas_nodes;
+        ng = make_uint2((uint32_t)__ldg(&in->blas_root), 0x80000000u);
+        tg = make_uint2(0u, 0u);
         continue;
       }
-    } else {
-      in_blas = false;
-      setup_space(rs, wo, wd);
     }
-    if (sp == 0) break;
-    cur = stack[--sp];
+    if (ng.y <= 0x00FFFFFFu) {
+      if (in_blas && sp == blas_sp) {  // this instance is exhausted: back to world space
+        in_blas = false;
+        nodes = sc.tlas_nodes;
+        setup_space(rs, wo, wd);
+      }
+      if (sp == 0) break;
+      ng = stack[--sp];
+    }
   }
   return found;
 }

@@ -116,5 +116,7 @@ def test_bvh_build_stats(gpu_ctx):
     ms = sc.upload(gpu_ctx)
     st = gpu_ctx.accel_stats()
     n_tris = sum(len(i) // 3 for _, i in sc.meshes)
-    assert st["leaf_prims"] == n_tris and st["nodes"] == sum(max(len(i) // 3 - 1, 1) for _, i in sc.meshes)
+    # every triangle sits in exactly one primitive slot; an 8-wide node with <= 3 triangles per leaf needs far
+    # fewer nodes than the binary hierarchy it was collapsed from
+    assert st["leaf_prims"] == n_tris and len(sc.meshes) <= st["nodes"] <= n_tris // 4 and st["tlas_nodes"] >= 1
     assert 0 < ms < 1000 and st["sah_cost"] > 0
