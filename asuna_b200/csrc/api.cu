@@ -7,6 +7,7 @@
 // ≙ OutputImages.  There is no CPU fallback: without a CUDA device asuna_create fails.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -68,6 +69,7 @@ struct asuna_ctx {
   BuildScratch scratch;
   uint64_t accel_stats[4] = {0, 0, 0, 0};
   bool may_pass_through = false;
+  uint32_t kind_mask = 0;  // hit kinds that can occur in this scene (which shade kernels to launch)
 
   // frame state
   AsunaCamera cam{};
@@ -184,6 +186,9 @@ void free_path_buffers(asuna_ctx* ctx) {
   free_dev(ctx->ps.sh_l);
   free_dev(ctx->ps.queue[0]);
   free_dev(ctx->ps.queue[1]);
+  free_dev(ctx->ps.kind);
+  free_dev(ctx->ps.sorted);
+  free_dev(ctx->ps.bin_hist);
   ctx->path_capacity = 0;
 }
 
@@ -201,6 +206,9 @@ int ensure_path_buffers(asuna_ctx* ctx, uint32_t n_paths) {
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sh_l, n * sizeof(float4)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.queue[0], n * sizeof(uint32_t)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.queue[1], n * sizeof(uint32_t)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.kind, n));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sorted, n * sizeof(uint32_t)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.bin_hist, ((n + kBinTile - 1) / kBinTile) * kNumKinds * sizeof(uint32_t)));
   ctx->path_capacity = n_paths;
   return 0;
 }
@@ -507,13 +515,18 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   cudaEventCreate(&e1);
   cudaEventRecord(e0, s);
   // bottom level: one wide BVH per mesh (≙ createBottomLevelAS)
+  float cost_prim = 0.3f;  // SAH: one triangle test relative to one wide-node step
+  if (const char* t = getenv("ASUNA_TUNE")) {
+    unsigned a, b, c = 0;
+    if (sscanf(t, "%u,%u,%u", &a, &b, &c) == 3 && c > 0) cost_prim = 0.1f * (float)c;
+  }
   for (uint32_t i = 0; i < n_mesh; i++) {
     HostMesh& m = ctx->meshes[i];
     launch_tri_boxes(s, m.d_vertices, m.d_indices, m.n_tris, ctx->scratch);
     PrimPayload pl;
     pl.vertices = m.d_vertices, pl.indices = m.d_indices, pl.tris = ctx->d_tris;
     ASUNA_CUDA_CHECK(launch_build_wide(s, m.n_tris, ctx->d_blas_nodes, (uint32_t)m.node_base, (uint32_t)m.tri_base, ctx->scratch,
-                                       pl, 0.3f, ctx->d_mesh_lo + i, ctx->d_mesh_hi + i, ctx->d_build_results + i));
+                                       pl, cost_prim, ctx->d_mesh_lo + i, ctx->d_mesh_hi + i, ctx->d_build_results + i));
   }
   // top level over the instance boxes (≙ createTopLevelAS); entering an instance costs a ray transform
   // plus a whole mesh BVH, so leaves are kept to single instances wherever the SAH allows
@@ -558,6 +571,15 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   ctx->view.textures = ctx->d_textures;
   for (int k = 0; k < 3; k++) ctx->view.env[k] = DTexture{ctx->env[k].d_texels, (int)ctx->env[k].w, (int)ctx->env[k].h};
   ctx->view.n_instances = n_inst;
+  ctx->view.magic = 0x4B000000u;
+  ctx->view.refill_lanes = 8, ctx->view.tri_vote_shift = 2;
+  if (const char* t = getenv("ASUNA_TUNE")) {  // "refill,shift[,cost_prim x10]" -- traversal tuning experiments
+    unsigned a = 8, b = 2, c = 0;
+    if (sscanf(t, "%u,%u,%u", &a, &b, &c) >= 1) ctx->view.refill_lanes = std::min(std::max(a, 1u), 32u), ctx->view.tri_vote_shift = std::min(b, 5u);
+  }
+  ctx->kind_mask = 1u << kKindMiss;
+  for (auto& in : ctx->instances)
+    ctx->kind_mask |= in.light >= 0 ? (1u << kKindLight) : (1u << (kKindMaterial0 + ctx->materials[in.material].type));
   ctx->may_pass_through = false;
   for (auto& m : ctx->materials)
     if ((m.type == ASUNA_MAT_PBR_METALNESS_ROUGHNESS && (m.opacityTextureId >= 0 || m.specular > 0.f)) ||
@@ -622,13 +644,14 @@ static int render_batch(asuna_ctx* ctx, const int* frames, uint32_t n_frames) {
     }
     {
       ScopedTimer t(ctx, 1);
-      launch_shade(s, ctx->dims, ctx->view, fp, ctx->ps, ctx->out, ctx->d_counters, iter, qsel);
+      ctx->stats.kernel_launches += launch_shade(s, ctx->dims, ctx->view, fp, ctx->ps, ctx->out, ctx->d_counters, iter, qsel,
+                                                 ctx->kind_mask, n_paths);
     }
     {
       ScopedTimer t(ctx, 3);
       launch_trace_shadow(s, ctx->dims, ctx->view, ctx->ps, ctx->d_counters, iter);
     }
-    ctx->stats.kernel_launches += 3;
+    ctx->stats.kernel_launches += 2;
     ctx->stats.closest_launches += 1;
     iter++;
     qsel ^= 1;
@@ -763,7 +786,7 @@ int asuna_trace_rays(asuna_ctx* ctx, const float* rays, uint32_t n, float* tuv, 
   int rc = upload_user_rays(ctx, rays, n);
   if (rc) return rc;
   ASUNA_CUDA_CHECK(cudaMemsetAsync(&ctx->d_counters->stack_overflow, 0, sizeof(uint32_t), ctx->stream));
-  launch_trace_user(ctx->stream, ctx->view, ctx->d_user_rays, n, ctx->d_user_tuv, ctx->d_user_ip, nullptr, ctx->d_counters);
+  launch_trace_user(ctx->stream, ctx->dims, ctx->view, ctx->d_user_rays, n, ctx->d_user_tuv, ctx->d_user_ip, nullptr, ctx->d_counters);
   if (tuv) ASUNA_CUDA_CHECK(cudaMemcpyAsync(tuv, ctx->d_user_tuv, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(ip, ctx->d_user_ip, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
@@ -776,7 +799,7 @@ int asuna_occlusion_rays(asuna_ctx* ctx, const float* rays, uint32_t n, uint8_t*
   cudaSetDevice(ctx->device);
   int rc = upload_user_rays(ctx, rays, n);
   if (rc) return rc;
-  launch_trace_user(ctx->stream, ctx->view, ctx->d_user_rays, n, nullptr, nullptr, ctx->d_user_occ, ctx->d_counters);
+  launch_trace_user(ctx->stream, ctx->dims, ctx->view, ctx->d_user_rays, n, nullptr, nullptr, ctx->d_user_occ, ctx->d_counters);
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(occ, ctx->d_user_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ASUNA_CUDA_CHECK(cudaGetLastError());
@@ -791,7 +814,7 @@ int asuna_trace_primary(asuna_ctx* ctx, uint32_t* ip, float* t) {
   if (rc) return rc;
   FrameParams fp = make_frame_params(ctx);
   launch_primary_rays(ctx->stream, fp, ctx->d_user_rays);
-  launch_trace_user(ctx->stream, ctx->view, ctx->d_user_rays, n, ctx->d_user_tuv, ctx->d_user_ip, nullptr, ctx->d_counters);
+  launch_trace_user(ctx->stream, ctx->dims, ctx->view, ctx->d_user_rays, n, ctx->d_user_tuv, ctx->d_user_ip, nullptr, ctx->d_counters);
   std::vector<float> tuv((size_t)n * 3);
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(tuv.data(), ctx->d_user_tuv, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(ip, ctx->d_user_ip, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -18,6 +18,7 @@
 #include <cfloat>
 
 #include "bvh_build.cuh"
+#include "scan.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -152,43 +153,6 @@ __global__ void __launch_bounds__(kThreads) k_sort_hist(const uint64_t* __restri
   }
   __syncthreads();
   hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
-}
-
-// Exclusive scan of `total` counters in place, one 1024-thread block walking the array.
-__global__ void __launch_bounds__(1024) k_sort_scan(uint32_t* __restrict__ hist, uint32_t total) {
-  __shared__ uint32_t warp_sums[32];
-  __shared__ uint32_t carry;
-  if (threadIdx.x == 0) carry = 0;
-  __syncthreads();
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < total; base += 1024) {
-    uint32_t i = base + threadIdx.x;
-    uint32_t v = i < total ? hist[i] : 0u;
-    uint32_t s = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o);
-      if (lane >= o) s += t;
-    }
-    if (lane == 31) warp_sums[warp] = s;
-    __syncthreads();
-    if (warp == 0) {
-      uint32_t w = warp_sums[lane], ws = w;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        uint32_t t = __shfl_up_sync(0xFFFFFFFFu, ws, o);
-        if (lane >= o) ws += t;
-      }
-      warp_sums[lane] = ws - w;  // exclusive
-    }
-    __syncthreads();
-    uint32_t c = carry;
-    uint32_t excl = c + warp_sums[warp] + s - v;
-    if (i < total) hist[i] = excl;
-    __syncthreads();
-    if (threadIdx.x == 1023) carry = excl + v;
-    __syncthreads();
-  }
 }
 
 __global__ void __launch_bounds__(kThreads) k_sort_scatter(const uint64_t* __restrict__ keys_in,
@@ -771,7 +735,7 @@ static void sort_passes(cudaStream_t s, uint32_t n, BuildScratch& sc) {
   int cur = 0;
   for (int shift = 0; shift < 64; shift += 8) {
     k_sort_hist<<<sort_blocks, kThreads, 0, s>>>(sc.keys[cur], n, shift, sc.hist, sort_blocks);
-    k_sort_scan<<<1, 1024, 0, s>>>(sc.hist, 256u * sort_blocks);
+    k_scan_exclusive<<<1, 1024, 0, s>>>(sc.hist, 256u * sort_blocks);
     k_sort_scatter<<<sort_blocks, kThreads, 0, s>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1], sc.vals[cur ^ 1],
                                                     n, shift, sc.hist, sort_blocks);
     cur ^= 1;

@@ -85,6 +85,9 @@ struct SceneView {
   const DTexture* textures;
   DTexture env[3];                // env, marginal, conditional
   uint32_t n_instances;
+  uint32_t magic;                 // 0x4B000000 from the constant bank: keeps the PRMT selectors immediate (traverse.cuh)
+  uint32_t refill_lanes;          // traversal tuning (ASUNA_TUNE): refill when this many lanes are idle
+  uint32_t tri_vote_shift;        // triangle step quorum = live lanes >> shift
 };
 
 // ---- wavefront path state (structure of float4 arrays, one slot per in-flight path) -------
@@ -98,7 +101,15 @@ struct PathState {
   float4* sh_d;    //               d.xyz, w = path slot (bits)
   float4* sh_l;    //               NEE radiance to add if unoccluded
   uint32_t* queue[2];
+  uint8_t* kind;     // per queue index: what the closest-hit ray found (HitKind), written by the trace kernel
+  uint32_t* sorted;  // the current queue regrouped by kind (counting sort), consumed by the per-kind shade kernels
+  uint32_t* bin_hist;  // [kNumKinds][bin blocks] counts, then exclusive offsets
 };
+
+// What a closest-hit ray found: the reference dispatches on instanceShaderBindingTableRecordOffset = material type
+// (src/pipeline/pipeline_raytrace.cpp:134-140); here the hit queue is regrouped by this key instead.
+enum HitKind : uint32_t { kKindMiss = 0, kKindLight = 1, kKindMaterial0 = 2 /* + AsunaMaterialType */, kNumKinds = 16 };
+constexpr uint32_t kBinTile = 8192;  // queue entries per block of the binning kernels
 
 // Per-iteration device counters; one slot per bounce iteration so no reset kernel is needed.
 #define ASUNA_MAX_ITERS 256

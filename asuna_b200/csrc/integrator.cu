@@ -14,251 +14,94 @@
 // kernels are persistent with warp-granular dynamic work fetch.  No tensor cores: nothing here
 // is a dense contraction.  B200 has no RT cores, so traversal is a software stack walk over the
 // BVH built by bvh_build.cu with a watertight ray/triangle test (Woop, Benthin, Wald 2013).
+#include <algorithm>
+#include <utility>
+
 #include "integrator.cuh"
+#include "scan.cuh"
 #include "shading.cuh"
+#include "traverse.cuh"
 
 namespace asuna {
 
 namespace {
 
-constexpr int kTraceThreads = 128;
 constexpr int kShadeThreads = 128;
-constexpr int kStackSize = 40;  // uint2 entries: wide-BVH depth of the instance level + one mesh level
 
-struct HitRec {
-  float t, b1, b2;
-  uint32_t inst, prim;
+// ---- trace kernels: persistent warps over the ray queues (traverse.cuh) -------------------------
+struct ClosestPolicy {  // rgen:108-109: tmin 1e-5, tmax 1e10; the hit record goes back into the path slot
+  PathState ps;
+  const uint32_t* queue;
+  const DInstance* instances;
+  ADEV void load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
+    const uint32_t slot = queue[i];
+    o = f3(ps.ray_o[slot]), d = f3(ps.ray_d[slot]);
+    tmin = kMinimum, tmax = kInfinity;
+  }
+  ADEV void commit(uint32_t i, bool, const HitRec& h) const {
+    ps.hit[queue[i]] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), h.inst, h.prim);
+    uint32_t kind = kKindMiss;  // the key the hit queue is regrouped by before shading
+    if (h.inst != 0xFFFFFFFFu) {
+      const uint32_t mt = __ldg(&instances[h.inst].mat_type);
+      kind = mt == 0xFFFFFFFFu ? (uint32_t)kKindLight : kKindMaterial0 + mt;
+    }
+    ps.kind[i] = (uint8_t)kind;
+  }
 };
 
-ADEV float safe_rcp(float d) { return 1.0f / (fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)); }
-
-struct RaySpace {  // ray constants in the space being traversed (world or one instance's object space)
-  float3 o, idir;
-  int kx, ky, kz;       // watertight test: axis permutation
-  float Sx, Sy, Sz;     // and shear
-  float3 d;
-  uint32_t octinv4;     // (7 ^ octant) replicated in the four bytes; octant bit k = direction negative on axis k
+struct ShadowPolicy {  // rgen:117-125: tmin 0, tmax = dist - 2 EPS, first hit ends it; unoccluded adds dRec.radiance
+  PathState ps;
+  ADEV void load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
+    const float4 a = ps.sh_o[i];
+    o = f3(a), d = f3(ps.sh_d[i]);
+    tmin = 0.0f, tmax = a.w;
+  }
+  ADEV void commit(uint32_t i, bool occluded, const HitRec&) const {
+    if (occluded) return;
+    const uint32_t slot = __float_as_uint(ps.sh_d[i].w);
+    const float4 L = ps.sh_l[i], r = ps.rad[slot];
+    ps.rad[slot] = make_float4(r.x + L.x, r.y + L.y, r.z + L.z, r.w);
+  }
 };
 
-ADEV void setup_shear(RaySpace& r) {
-  float ax = fabsf(r.d.x), ay = fabsf(r.d.y), az = fabsf(r.d.z);
-  r.kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-  r.kx = r.kz == 2 ? 0 : r.kz + 1;
-  r.ky = r.kx == 2 ? 0 : r.kx + 1;
-  float dz = comp(r.d, r.kz);
-  if (dz < 0.0f) {
-    int t = r.kx;
-    r.kx = r.ky;
-    r.ky = t;
+struct UserPolicy {  // asuna_trace_rays / asuna_occlusion_rays / asuna_trace_primary (parity tests)
+  const float4* rays;
+  float* tuv;
+  uint32_t* inst_prim;
+  uint8_t* occluded;
+  ADEV void load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
+    const float4 a = rays[2 * i], b = rays[2 * i + 1];
+    o = f3(a), d = f3(b), tmin = a.w, tmax = b.w;
   }
-  r.Sx = comp(r.d, r.kx) / dz;
-  r.Sy = comp(r.d, r.ky) / dz;
-  r.Sz = 1.0f / dz;
-}
-ADEV void setup_space(RaySpace& r, float3 o, float3 d) {
-  r.o = o;
-  r.d = d;
-  r.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-  uint32_t oct = (r.idir.x < 0.f ? 1u : 0u) | (r.idir.y < 0.f ? 2u : 0u) | (r.idir.z < 0.f ? 4u : 0u);
-  r.octinv4 = (7u ^ oct) * 0x01010101u;
-}
-
-ADEV float byte_f(uint32_t v, int j) { return (float)((v >> (8 * j)) & 0xFFu); }
-
-// Slab test of the eight quantised child boxes of one compressed wide node (Ylitie et al. 2017, section 3):
-// plane t = q * (2^e / d) + (p - o) / d.  Returns the hit mask: inner children set bit 24 + (slot ^ octinv)
-// (so the highest set bit is the nearest octant), leaf children set their primitive bits [offset, offset+count).
-// The far plane is widened by 2 ulp so the box never rejects what the watertight triangle test accepts.
-ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 n4, const RaySpace& r, float tmin,
-                                  float tmax) {
-  const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * r.idir.x;
-  const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * r.idir.y;
-  const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * r.idir.z;
-  const float bx = (__uint_as_float(n0.x) - r.o.x) * r.idir.x;
-  const float by = (__uint_as_float(n0.y) - r.o.y) * r.idir.y;
-  const float bz = (__uint_as_float(n0.z) - r.o.z) * r.idir.z;
-  const bool nx = r.idir.x < 0.f, ny = r.idir.y < 0.f, nz = r.idir.z < 0.f;
-  uint32_t hitmask = 0;
-#pragma unroll
-  for (int h = 0; h < 2; h++) {
-    const uint32_t meta4 = h ? n1.w : n1.z;
-    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const uint32_t inner_mask4 = (is_inner4 >> 4) * 0xFFu;
-    const uint32_t bit_index4 = (meta4 ^ (r.octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
-    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
-    const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
-    const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
-    const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
-    const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
-    const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      float tnx = fmaf(byte_f(nearx, j), ax, bx), tfx = fmaf(byte_f(farx, j), ax, bx);
-      float tny = fmaf(byte_f(neary, j), ay, by), tfy = fmaf(byte_f(fary, j), ay, by);
-      float tnz = fmaf(byte_f(nearz, j), az, bz), tfz = fmaf(byte_f(farz, j), az, bz);
-      float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));
-      float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));
-      if (cmin <= cmax * 1.0000004f)
-        hitmask |= ((child_bits4 >> (8 * j)) & 0xFFu) << ((bit_index4 >> (8 * j)) & 0xFFu);
+  ADEV void commit(uint32_t i, bool found, const HitRec& h) const {
+    if (occluded) {
+      occluded[i] = found ? 1 : 0;
+      return;
     }
+    if (tuv) tuv[3 * i] = found ? h.t : 0.f, tuv[3 * i + 1] = h.b1, tuv[3 * i + 2] = h.b2;
+    inst_prim[2 * i] = h.inst, inst_prim[2 * i + 1] = h.prim;
   }
-  return hitmask;
-}
+};
 
-// Watertight ray/triangle test, no culling.  Barycentrics in the Vulkan convention.
-ADEV bool hit_triangle(const RaySpace& r, float3 v0, float3 v1, float3 v2, float& t, float& b1, float& b2) {
-  float3 A = v0 - r.o, B = v1 - r.o, C = v2 - r.o;
-  float Akz = comp(A, r.kz), Bkz = comp(B, r.kz), Ckz = comp(C, r.kz);
-  float Ax = comp(A, r.kx) - r.Sx * Akz, Ay = comp(A, r.ky) - r.Sy * Akz;
-  float Bx = comp(B, r.kx) - r.Sx * Bkz, By = comp(B, r.ky) - r.Sy * Bkz;
-  float Cx = comp(C, r.kx) - r.Sx * Ckz, Cy = comp(C, r.ky) - r.Sy * Ckz;
-  // Edge functions with individually rounded products (no FMA contraction): the neighbour across a
-  // shared edge then computes the exact negative, which is what makes the test watertight.
-  float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
-  float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
-  float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
-  if (U == 0.0f || V == 0.0f || W == 0.0f) {  // edge case: redo the edge functions in double
-    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
-    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
-    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
-  }
-  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
-  float det = U + V + W;
-  if (det == 0.0f) return false;
-  float T = U * (r.Sz * Akz) + V * (r.Sz * Bkz) + W * (r.Sz * Ckz);
-  float inv = 1.0f / det;
-  t = T * inv;
-  b1 = V * inv;
-  b2 = W * inv;
-  return true;
-}
-
-// Two-level traversal with traceRayEXT semantics: per instance the ray is taken into object space
-// (origin and unnormalised direction through world->object), t is shared between spaces.
-// Ties are broken toward the lower (instance, primitive) pair, as the oracle defines.
-// Stack entries are (base index, mask) groups: mask > 0x00FFFFFF = a node group (hit bits of inner
-// children in the top byte, imask in the low byte), otherwise a primitive group (<= 24 hit bits).
-template <bool ANY, bool COUNT = false>
-__device__ bool traverse(const SceneView& sc, float3 wo, float3 wd, float tmin, float tmax, HitRec& best,
-                         uint32_t* overflow, uint32_t* n_nodes = nullptr, uint32_t* n_tris = nullptr) {
-  if (sc.n_instances == 0) return false;
-  uint2 stack[kStackSize];
-  int sp = 0, blas_sp = 0;
-  RaySpace rs;
-  setup_space(rs, wo, wd);
-  bool in_blas = false, found = false;
-  uint32_t cur_inst = 0;
-  const WideNode* nodes = sc.tlas_nodes;
-  uint2 ng = make_uint2(0u, 0x80000000u), tg = make_uint2(0u, 0u);
-  for (;;) {
-    if (ng.y > 0x00FFFFFFu) {
-      const uint32_t hits = ng.y;
-      const uint32_t bit = 31u - (uint32_t)__clz(hits);
-      ng.y &= ~(1u << bit);
-      if (ng.y > 0x00FFFFFFu) {
-        if (sp < kStackSize) stack[sp++] = ng;
-        else atomicAdd(overflow, 1u);
-      }
-      const uint32_t slot = (bit - 24u) ^ (rs.octinv4 & 7u);
-      const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
-      const uint4* np = reinterpret_cast<const uint4*>(nodes + ng.x + rel);
-      if (COUNT) (*n_nodes)++;
-      const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
-      const uint32_t hm = intersect_wide_node(n0, n1, n2, n3, n4, rs, tmin, tmax);
-      ng = make_uint2(n1.x, (hm & 0xFF000000u) | (n0.w >> 24));
-      tg = make_uint2(n1.y, hm & 0x00FFFFFFu);
-    } else {
-      tg = ng;
-      ng = make_uint2(0u, 0u);
-    }
-    if (in_blas) {
-      while (tg.y) {
-        const uint32_t k = (uint32_t)__ffs((int)tg.y) - 1u;
-        tg.y &= tg.y - 1u;
-        const TriSlot* tp = sc.tris + tg.x + k;
-        float4 v0 = __ldg(&tp->v0), v1 = __ldg(&tp->v1), v2 = __ldg(&tp->v2);
-        float t, b1, b2;
-        if (COUNT) (*n_tris)++;
-        if (!hit_triangle(rs, f3(v0), f3(v1), f3(v2), t, b1, b2)) continue;
-        if (!(t > tmin)) continue;
-        uint32_t prim = __float_as_uint(v0.w);
-        bool closer = t < tmax || (t == tmax && found &&
-                                   (cur_inst < best.inst || (cur_inst == best.inst && prim < best.prim)));
-        if (!closer) continue;
-        best.t = t, best.b1 = b1, best.b2 = b2, best.inst = cur_inst, best.prim = prim;
-        tmax = t;
-        found = true;
-        if (ANY) return true;
-      }
-    } else if (tg.y) {
-      // instance group: enter the first instance, keep the rest (and the pending node group) for later
-      const uint32_t k = (uint32_t)__ffs((int)tg.y) - 1u;
-      tg.y &= tg.y - 1u;
-      if (sp + 2 > kStackSize) {
-        atomicAdd(overflow, 1u);
-      } else {
-        if (tg.y) stack[sp++] = tg;
-        if (ng.y > 0x00FFFFFFu) stack[sp++] = ng;
-        cur_inst = __ldg(&sc.tlas_leaf_inst[tg.x + k]);
-        const DInstance* in = sc.instances + cur_inst;
-        float4 r0 = __ldg(&in->w2o[0]), r1 = __ldg(&in->w2o[1]), r2 = __ldg(&in->w2o[2]);
-        float4 m[3] = {r0, r1, r2};
-        setup_space(rs, xf_point(m, wo), xf_vector(m, wd));
-        setup_shear(rs);
-        in_blas = true;
-        blas_sp = sp;
-        nodes = sc.blas_nodes;
-        ng = make_uint2((uint32_t)__ldg(&in->blas_root), 0x80000000u);
-        tg = make_uint2(0u, 0u);
-        continue;
-      }
-    }
-    if (ng.y <= 0x00FFFFFFu) {
-      if (in_blas && sp == blas_sp) {  // this instance is exhausted: back to world space
-        in_blas = false;
-        nodes = sc.tlas_nodes;
-        setup_space(rs, wo, wd);
-      }
-      if (sp == 0) break;
-      ng = stack[--sp];
-    }
-  }
-  return found;
-}
-
-// ---- trace kernels: persistent, warp-granular dynamic fetch -----------------------------------
 template <bool COUNT>
 __global__ void __launch_bounds__(kTraceThreads)
 k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter, int qsel) {
-  const uint32_t count = cnt->queue[iter];
-  const uint32_t* queue = ps.queue[qsel];
-  const int lane = threadIdx.x & 31;
-  uint32_t n_nodes = 0, n_tris = 0;
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&cnt->ticket_closest[iter], 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= count) break;
-    uint32_t i = base + lane;
-    if (i < count) {
-      uint32_t slot = queue[i];
-      float4 o = ps.ray_o[slot], d = ps.ray_d[slot];
-      HitRec h;
-      h.inst = 0xFFFFFFFFu, h.prim = 0xFFFFFFFFu, h.b1 = h.b2 = h.t = 0.f;
-      traverse<false, COUNT>(sc, f3(o), f3(d), kMinimum, kInfinity, h, &cnt->stack_overflow, &n_nodes, &n_tris);
-      ps.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), h.inst, h.prim);
-    }
-  }
-  if (COUNT) {
-    for (int o = 16; o > 0; o >>= 1) {
-      n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, o);
-      n_tris += __shfl_xor_sync(0xFFFFFFFFu, n_tris, o);
-    }
-    if (lane == 0) {
-      atomicAdd(&cnt->node_visits, (unsigned long long)n_nodes);
-      atomicAdd(&cnt->tri_tests, (unsigned long long)n_tris);
-    }
-  }
+  ClosestPolicy pol{ps, ps.queue[qsel], sc.instances};
+  trace_persistent<false, COUNT>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow,
+                                 &cnt->node_visits, &cnt->tri_tests);
+}
+
+__global__ void __launch_bounds__(kTraceThreads)
+k_trace_shadow(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter) {
+  ShadowPolicy pol{ps};
+  trace_persistent<true, false>(sc, pol, cnt->shadow[iter], &cnt->ticket_shadow[iter], &cnt->stack_overflow, nullptr,
+                                nullptr);
+}
+
+template <bool ANY>
+__global__ void __launch_bounds__(kTraceThreads)
+k_trace_user(const __grid_constant__ SceneView sc, UserPolicy pol, uint32_t n, uint32_t* ticket, Counters* cnt) {
+  trace_persistent<ANY, false>(sc, pol, n, ticket, &cnt->stack_overflow, nullptr, nullptr);
 }
 
 // Adds one batch's per-iteration counters into the persistent totals (one thread; a few hundred words).
@@ -271,46 +114,6 @@ __global__ void k_fold_counters(const Counters* cnt, Totals* tot, int iters) {
   tot->node_visits += cnt->node_visits;
   tot->tri_tests += cnt->tri_tests;
   tot->stack_overflow += cnt->stack_overflow;
-}
-
-__global__ void __launch_bounds__(kTraceThreads) k_trace_shadow(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter) {
-  const uint32_t count = cnt->shadow[iter];
-  const int lane = threadIdx.x & 31;
-  for (;;) {
-    uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(&cnt->ticket_shadow[iter], 32u);
-    base = __shfl_sync(0xFFFFFFFFu, base, 0);
-    if (base >= count) break;
-    uint32_t i = base + lane;
-    if (i < count) {
-      float4 o = ps.sh_o[i], d = ps.sh_d[i];
-      HitRec h;
-      // rgen:117-122: tmin 0, tmax = dist - 2 EPS, terminate on first hit
-      bool occluded = traverse<true>(sc, f3(o), f3(d), 0.0f, o.w, h, &cnt->stack_overflow);
-      if (!occluded) {
-        uint32_t slot = __float_as_uint(d.w);
-        float4 L = ps.sh_l[i], r = ps.rad[slot];
-        ps.rad[slot] = make_float4(r.x + L.x, r.y + L.y, r.z + L.z, r.w);
-      }
-    }
-  }
-}
-
-// Generic ray queries for the parity tests (asuna_trace_rays / asuna_occlusion_rays / asuna_trace_primary).
-__global__ void k_trace_user(const __grid_constant__ SceneView sc, const float4* rays, uint32_t n, float* tuv, uint32_t* inst_prim,
-                             uint8_t* occluded, Counters* cnt) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float4 a = rays[2 * i], b = rays[2 * i + 1];
-  HitRec h;
-  h.inst = 0xFFFFFFFFu, h.prim = 0xFFFFFFFFu, h.b1 = h.b2 = h.t = 0.f;
-  if (occluded) {
-    occluded[i] = traverse<true>(sc, f3(a), f3(b), a.w, b.w, h, &cnt->stack_overflow) ? 1 : 0;
-  } else {
-    bool f = traverse<false>(sc, f3(a), f3(b), a.w, b.w, h, &cnt->stack_overflow);
-    if (tuv) tuv[3 * i] = f ? h.t : 0.f, tuv[3 * i + 1] = h.b1, tuv[3 * i + 2] = h.b2;
-    inst_prim[2 * i] = h.inst, inst_prim[2 * i + 1] = h.prim;
-  }
 }
 
 // ---- camera: raytrace.projective.rgen:41-87 ---------------------------------------------------
@@ -384,11 +187,76 @@ ADEV void load_surface(const SceneView& sc, const AsunaState& pc, const DInstanc
   configure_frame(pc, s);
 }
 
+// ---- regroup the hit queue by kind: one counting-sort pass (histogram / scan / stable scatter) ----
+// The RT pipeline of the reference picks the closest-hit shader per instance through the shader binding
+// table; the wavefront equivalent is a queue per shader.  Keys are the bytes the trace kernel left in
+// ps.kind, values the path slots; kNumKinds bins.
+__global__ void __launch_bounds__(256) k_bin_count(PathState ps, const Counters* cnt, int iter, uint32_t n_blocks) {
+  __shared__ uint32_t h[kNumKinds];
+  if (threadIdx.x < kNumKinds) h[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t count = cnt->queue[iter], base = blockIdx.x * kBinTile;
+  if (base < count) {
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t i = base + threadIdx.x; i < base + kBinTile; i += 256) {  // uniform trip count
+      uint32_t k = i < count ? ps.kind[i] : kNumKinds + lane;
+      uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
+      if (i < count && lane == (uint32_t)__ffs((int)peers) - 1u) atomicAdd(&h[k], (uint32_t)__popc(peers));
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumKinds) ps.bin_hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(256) k_bin_scatter(PathState ps, const Counters* cnt, int iter, int qsel, uint32_t n_blocks) {
+  constexpr int kWarps = 8, kRounds = kBinTile / kWarps / 32;
+  __shared__ uint32_t wh[kWarps][kNumKinds];
+  const uint32_t count = cnt->queue[iter], base = blockIdx.x * kBinTile;
+  if (base >= count) return;
+  const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+  if (threadIdx.x < kWarps * kNumKinds) (&wh[0][0])[threadIdx.x] = 0;
+  __syncthreads();
+  const uint32_t* queue = ps.queue[qsel];
+  const uint32_t wbase = base + warp * (kRounds * 32);
+  for (int r = 0; r < kRounds; r++) {
+    uint32_t i = wbase + r * 32 + lane;
+    bool valid = i < count;
+    uint32_t k = valid ? ps.kind[i] : kNumKinds + lane;
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
+    if (valid && lane == (uint32_t)__ffs((int)peers) - 1u) wh[warp][k] += __popc(peers);
+    __syncwarp();
+  }
+  __syncthreads();
+  if (threadIdx.x < kNumKinds) {  // global offset of this block per kind, then exclusive over its warps
+    uint32_t run = ps.bin_hist[threadIdx.x * n_blocks + blockIdx.x];
+    for (int w = 0; w < kWarps; w++) {
+      uint32_t c = wh[w][threadIdx.x];
+      wh[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int r = 0; r < kRounds; r++) {
+    uint32_t i = wbase + r * 32 + lane;
+    bool valid = i < count;
+    uint32_t k = valid ? ps.kind[i] : kNumKinds + lane;
+    uint32_t peers = __match_any_sync(0xFFFFFFFFu, k);
+    uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid) ps.sorted[wh[warp][k] + rank] = queue[i];
+    __syncwarp();
+    if (valid && lane == (uint32_t)__ffs((int)peers) - 1u) wh[warp][k] += __popc(peers);
+    __syncwarp();
+  }
+}
+
+// ---- shading: one kernel per hit kind (≙ one closest-hit / miss shader each) -----------------------
+template <uint32_t KIND>
 __global__ void __launch_bounds__(kShadeThreads)
 k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParams fp, PathState ps, OutputImages out, Counters* cnt, int iter,
-        int qsel) {
-  const uint32_t count = cnt->queue[iter];
-  const uint32_t* queue = ps.queue[qsel];
+        int qsel, uint32_t n_blocks) {
+  const uint32_t begin = ps.bin_hist[KIND * n_blocks];
+  const uint32_t end = KIND + 1 < kNumKinds ? ps.bin_hist[(KIND + 1) * n_blocks] : cnt->queue[iter];
+  const uint32_t* queue = ps.sorted;
   uint32_t* next_queue = ps.queue[qsel ^ 1];
   const int lane = threadIdx.x & 31;
   const uint32_t warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -403,9 +271,9 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
   se.env.res_y = fp.pc.envMapResolution[1];
   se.env.intensity = fp.pc.envMapIntensity;
 
-  for (uint32_t base = warp_global * 32; base < count; base += n_warps * 32) {
+  for (uint32_t base = begin + warp_global * 32; base < end; base += n_warps * 32) {
     uint32_t i = base + lane;
-    bool valid = i < count;
+    bool valid = i < end;
     bool cont = false, nee = false, incoherent = false;
     uint32_t slot = 0;
     PathRegs p;
@@ -413,7 +281,6 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
     if (valid) {
       slot = queue[i];
       float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot], th = ps.thr[slot], ra = ps.rad[slot];
-      uint4 hit = ps.hit[slot];
       uint32_t fi = slot / fp.n_pixels, pixel = slot - fi * fp.n_pixels;
       bool frame0 = fp.frame_ids[fi] == 0;
       for (int c = 0; c < ASUNA_NUM_OUTPUT_IMAGES - 1; c++) se.aov[c] = frame0 ? out.img[c + 1] : nullptr;
@@ -425,27 +292,27 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
       p.bsdf_flags = packed >> 16;
       p.stop = false;
       p.nee_L = f3(0.0f);
-      if (hit.z == 0xFFFFFFFFu) {
+      if constexpr (KIND == kKindMiss) {
         shade_miss(se, p);
       } else {
+        const uint4 hit = ps.hit[slot];
         const DInstance in = sc.instances[hit.z];
         Surface s;
         load_surface(sc, fp.pc, in, hit, p.ray_d, s);
-        if (in.light >= 0) {
+        if constexpr (KIND == kKindLight) {
           shade_light_hit(se, p, in.light, s.pos);
         } else {
           const AsunaMaterial m = sc.materials[in.material];
-          switch (m.type) {
-            case ASUNA_MAT_LAMBERTIAN: shade_lambertian(se, p, s, m, pixel); break;
-            case ASUNA_MAT_EMISSIVE: shade_emissive(se, p, s, m); break;
-            case ASUNA_MAT_DIELECTRIC: shade_dielectric(se, p, s, m); break;
-            case ASUNA_MAT_CONDUCTOR: shade_conductor(se, p, s, m); break;
-            case ASUNA_MAT_PLASTIC: shade_plastic(se, p, s, m); break;
-            case ASUNA_MAT_ROUGH_PLASTIC: shade_rough_plastic(se, p, s, m); break;
-            case ASUNA_MAT_PBR_METALNESS_ROUGHNESS: shade_pbr(se, p, s, m, pixel); break;
-            case ASUNA_MAT_KANG18: shade_kang18(se, p, s, m, in, pixel); break;
-            default: p.stop = true; break;
-          }
+          constexpr uint32_t T = KIND - kKindMaterial0;
+          if constexpr (T == ASUNA_MAT_LAMBERTIAN) shade_lambertian(se, p, s, m, pixel);
+          else if constexpr (T == ASUNA_MAT_EMISSIVE) shade_emissive(se, p, s, m);
+          else if constexpr (T == ASUNA_MAT_DIELECTRIC) shade_dielectric(se, p, s, m);
+          else if constexpr (T == ASUNA_MAT_CONDUCTOR) shade_conductor(se, p, s, m);
+          else if constexpr (T == ASUNA_MAT_PLASTIC) shade_plastic(se, p, s, m);
+          else if constexpr (T == ASUNA_MAT_ROUGH_PLASTIC) shade_rough_plastic(se, p, s, m);
+          else if constexpr (T == ASUNA_MAT_PBR_METALNESS_ROUGHNESS) shade_pbr(se, p, s, m, pixel);
+          else if constexpr (T == ASUNA_MAT_KANG18) shade_kang18(se, p, s, m, in, pixel);
+          else p.stop = true;
         }
       }
       // rgen:112-131: shadow ray if the hit shader asked for one, then stop / depth++
@@ -568,9 +435,39 @@ void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView&
 void launch_fold_counters(cudaStream_t s, const Counters* cnt, Totals* tot, int iters) {
   k_fold_counters<<<1, 1, 0, s>>>(cnt, tot, iters);
 }
-void launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const FrameParams& fp, const PathState& ps,
-                  const OutputImages& out, Counters* cnt, int iter, int qsel) {
-  k_shade<<<ld.shade_blocks, kShadeThreads, 0, s>>>(sc, fp, ps, out, cnt, iter, qsel);
+template <uint32_t KIND>
+static void launch_shade_kind(cudaStream_t s, uint32_t blocks, const SceneView& sc, const FrameParams& fp, const PathState& ps,
+                              const OutputImages& out, Counters* cnt, int iter, int qsel, uint32_t nb) {
+  k_shade<KIND><<<blocks, kShadeThreads, 0, s>>>(sc, fp, ps, out, cnt, iter, qsel, nb);
+}
+using ShadeLauncher = void (*)(cudaStream_t, uint32_t, const SceneView&, const FrameParams&, const PathState&,
+                               const OutputImages&, Counters*, int, int, uint32_t);
+template <uint32_t... K>
+static void fill_launchers(ShadeLauncher* t, std::integer_sequence<uint32_t, K...>) {
+  ((t[K] = launch_shade_kind<K>), ...);
+}
+
+// Regroups the hit queue of this bounce by kind, then runs one shade kernel per kind present in the scene.
+// Returns the number of kernels launched.
+int launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const FrameParams& fp, const PathState& ps,
+                 const OutputImages& out, Counters* cnt, int iter, int qsel, uint32_t kind_mask, uint32_t n_paths) {
+  static ShadeLauncher table[kNumKinds];
+  static bool init = false;
+  if (!init) {
+    fill_launchers(table, std::make_integer_sequence<uint32_t, kNumKinds>{});
+    init = true;
+  }
+  const uint32_t nb = div_up(n_paths, kBinTile);
+  k_bin_count<<<nb, 256, 0, s>>>(ps, cnt, iter, nb);
+  k_scan_exclusive<<<1, 1024, 0, s>>>(ps.bin_hist, kNumKinds * nb);
+  k_bin_scatter<<<nb, 256, 0, s>>>(ps, cnt, iter, qsel, nb);
+  int launches = 3;
+  for (uint32_t k = 0; k < kNumKinds; k++)
+    if (kind_mask & (1u << k)) {
+      table[k](s, ld.shade_blocks[k], sc, fp, ps, out, cnt, iter, qsel, nb);
+      launches++;
+    }
+  return launches;
 }
 void launch_trace_shadow(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
                          int iter) {
@@ -588,9 +485,28 @@ void launch_import_partial(cudaStream_t s, const OutputImages& out, const float4
 void launch_primary_rays(cudaStream_t s, const FrameParams& fp, float4* rays) {
   k_primary_rays<<<div_up(fp.n_pixels, 256), 256, 0, s>>>(fp, rays);
 }
-void launch_trace_user(cudaStream_t s, const SceneView& sc, const float4* rays, uint32_t n, float* tuv,
+void launch_trace_user(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const float4* rays, uint32_t n, float* tuv,
                        uint32_t* inst_prim, uint8_t* occluded, Counters* cnt) {
-  k_trace_user<<<div_up(n, 128), 128, 0, s>>>(sc, rays, n, tuv, inst_prim, occluded, cnt);
+  // the user-ray ticket lives in the last slot of the shadow tickets (never reached by a render: ASUNA_MAX_ITERS)
+  uint32_t* ticket = &cnt->ticket_shadow[ASUNA_MAX_ITERS];
+  cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s);
+  UserPolicy pol{rays, tuv, inst_prim, occluded};
+  uint32_t blocks = std::min(ld.trace_blocks, std::max(1u, div_up(n, kTraceThreads)));
+  if (occluded) k_trace_user<true><<<blocks, kTraceThreads, 0, s>>>(sc, pol, n, ticket, cnt);
+  else k_trace_user<false><<<blocks, kTraceThreads, 0, s>>>(sc, pol, n, ticket, cnt);
+}
+
+template <uint32_t... K>
+static cudaError_t shade_occupancy(LaunchDims& ld, int sm_count, std::integer_sequence<uint32_t, K...>) {
+  cudaError_t err = cudaSuccess;
+  auto one = [&](auto kernel, uint32_t k) {
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kShadeThreads, 0);
+    if (e != cudaSuccess) err = e;
+    ld.shade_blocks[k] = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
+  };
+  (one(k_shade<K>, K), ...);
+  return err;
 }
 
 cudaError_t query_launch_dims(LaunchDims& ld, int sm_count) {
@@ -598,10 +514,7 @@ cudaError_t query_launch_dims(LaunchDims& ld, int sm_count) {
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest<false>, kTraceThreads, 0);
   if (e != cudaSuccess) return e;
   ld.trace_blocks = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
-  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_shade, kShadeThreads, 0);
-  if (e != cudaSuccess) return e;
-  ld.shade_blocks = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
-  return cudaSuccess;
+  return shade_occupancy(ld, sm_count, std::make_integer_sequence<uint32_t, kNumKinds>{});
 }
 
 }  // namespace asuna

@@ -10,7 +10,7 @@ struct OutputImages {
 
 struct LaunchDims {
   uint32_t trace_blocks = 0;  // persistent grids: SM count x resident blocks per SM
-  uint32_t shade_blocks = 0;
+  uint32_t shade_blocks[kNumKinds] = {};  // per hit kind (register use differs per material)
 };
 
 cudaError_t query_launch_dims(LaunchDims& ld, int sm_count);
@@ -19,15 +19,15 @@ void launch_raygen(cudaStream_t s, const FrameParams& fp, const PathState& ps, c
 void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
                           int iter, int qsel, bool counting);
 void launch_fold_counters(cudaStream_t s, const Counters* cnt, Totals* tot, int iters);
-void launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const FrameParams& fp, const PathState& ps,
-                  const OutputImages& out, Counters* cnt, int iter, int qsel);
+int launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const FrameParams& fp, const PathState& ps,
+                 const OutputImages& out, Counters* cnt, int iter, int qsel, uint32_t kind_mask, uint32_t n_paths);
 void launch_trace_shadow(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
                          int iter);
 void launch_accumulate(cudaStream_t s, const FrameParams& fp, const PathState& ps, const OutputImages& out);
 void launch_export_partial(cudaStream_t s, const OutputImages& out, float4* partial, uint32_t n, int have_accum);
 void launch_import_partial(cudaStream_t s, const OutputImages& out, const float4* partial, uint32_t n);
 void launch_primary_rays(cudaStream_t s, const FrameParams& fp, float4* rays);
-void launch_trace_user(cudaStream_t s, const SceneView& sc, const float4* rays, uint32_t n, float* tuv,
+void launch_trace_user(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const float4* rays, uint32_t n, float* tuv,
                        uint32_t* inst_prim, uint8_t* occluded, Counters* cnt);
 
 }  // namespace asuna

@@ -479,6 +479,26 @@ ADEV float3 sample_lights(const ShadeEnv& se, PathRegs& p, float3 pos, float3 no
   return radiance;
 }
 
+// For the delta BSDFs (dielectric, conductor) eval(..., EArea) is identically zero (A.3-4), so the direct-light
+// record of sampleLights never contributes: only its random-number consumption (A.1) has to be reproduced --
+// not the env-map / sun-sky / light evaluation behind it.
+ADEV void sample_lights_rng_only(const ShadeEnv& se, PathRegs& p) {
+  const AsunaState& pc = se.fp->pc;
+  bool has_env = (pc.hasEnvMap == 1 || se.fp->sunsky.in_use == 1);
+  bool has_light = (pc.numLights > 0);
+  float env_sel = has_env ? (has_light ? 0.5f : 1.0f) : 0.0f;
+  float ana_sel = has_light ? (has_env ? 0.5f : 1.0f) : 0.0f;
+  float sel = rnd(p.seed);
+  if (sel < env_sel) {
+    (void)rnd2(p.seed);
+  } else if (sel < env_sel + ana_sel) {
+    (void)rnd(p.seed);
+    (void)rnd2(p.seed);
+  }
+  p.nee = false;
+  p.nee_L = f3(0.0f);
+}
+
 ADEV void store_direct(PathRegs& p, bool visible, float3 w, float bsdf_pdf, float3 radiance, const LightSample& ls) {
   float3 Ld = f3(0.0f);
   if (visible) Ld = power_heuristic(ls.pdf, bsdf_pdf) * w * radiance * p.throughput / (ls.pdf + kEps);
@@ -624,20 +644,7 @@ ADEV void shade_dielectric(const ShadeEnv& se, PathRegs& p, Surface& s, const As
   apply_normal_map(se, m, s);
   float eta = dot(s.V, s.N) > 0.0f ? (1.0f / m.ior) : m.ior;
   float F = dielectric_fresnel(fabsf(dot(s.V, s.ffN)), eta);
-  {
-    bool visible;
-    LightSample ls;
-    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
-    float bpdf = 0.0f;  // eval(...,EArea) is identically 0 (A.3-4); pdf only matters for delta lights
-    if (visible && (ls.flags & kLightDelta)) {
-      if (dot(ls.d, s.ffN) > 0) {
-        if (fabsf(dot(reflect(-s.V, s.ffN), ls.d) - 1) < kEps) bpdf = F;
-      } else {
-        if (fabsf(dot(refract(-s.V, s.ffN, eta), ls.d) - 1) < kEps) bpdf = 1 - F;
-      }
-    }
-    store_direct(p, visible, f3(0.0f), bpdf, radiance, ls);
-  }
+  sample_lights_rng_only(se, p);  // :96-118: eval(...,EArea) = 0, the shadow ray it fires adds nothing
   float u = rnd(p.seed);
   float3 d, w;
   float pdf;
@@ -672,18 +679,7 @@ ADEV void shade_conductor(const ShadeEnv& se, PathRegs& p, Surface& s, const Asu
   float3 kd = diffuse_of(se, m, s);
   apply_normal_map(se, m, s);
   float3 eta = f3(m.radiance), k = f3(m.radianceFactor);
-  {
-    bool visible;
-    LightSample ls;
-    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
-    float bpdf = 0.0f;  // eval(...,EArea) = 0
-    if (visible) {
-      float NdotL = dot(ls.d, s.ffN), NdotV = dot(s.V, s.ffN);
-      if (!(NdotL < 0 || NdotV < 0 || (ls.flags & kLightDelta) == 0))
-        if (fabsf(dot(reflect(-s.V, s.ffN), ls.d) - 1) < kEps) bpdf = 1.0f;
-    }
-    store_direct(p, visible, f3(0.0f), bpdf, radiance, ls);
-  }
+  sample_lights_rng_only(se, p);  // :107-133: eval(...,EArea) = 0
   (void)rnd2(p.seed);  // sampleBsdf takes a vec2 it never uses (:68)
   float NdotV = dot(s.V, s.ffN);
   if (NdotV <= 0) {

@@ -1,0 +1,361 @@
+// Ray traversal of the two-level compressed wide BVH, hand-written for sm_100a (no RT cores on B200).
+//
+// Replaces traceRayEXT of the reference (src/shaders/raytrace.projective.rgen:108-109 closest hit,
+// :117-122 shadow ray).  Semantics kept: per instance the ray is taken into object space (origin and
+// unnormalised direction through world->object) and t is shared between spaces; no culling; all
+// geometry opaque.  Ties (unspecified by Vulkan) go to the lower (instance, primitive) pair, as the
+// oracle defines.  The triangle test is the watertight test of Woop, Benthin, Wald 2013 written
+// without the axis permutation (three constant vectors per ray instead), bit-identical to
+// oracle/bvh.h.
+//
+// Execution model: persistent warps.  Every lane owns one ray at a time; the warp loops over
+//   pop / leave instance / terminate  ->  one wide-node step  ->  instance entry  ->  one triangle step
+// where the triangle step only runs when a quarter of the live lanes want it (or nothing else is left):
+// lanes with a pending triangle group swap it under the next node group of their stack and keep
+// traversing ("triangle postponing", Ylitie et al. 2017 section 5).  Finished lanes are refilled from the
+// ray queue with one atomic per warp as soon as `refill_lanes` of them are idle.
+#pragma once
+#include "device_types.cuh"
+#include "vec.cuh"
+
+namespace asuna {
+
+constexpr int kTraceThreads = 128;
+constexpr int kStackSize = 40;        // uint2 entries: wide-BVH depth of the instance level + one mesh level
+
+struct HitRec {
+  float t, b1, b2;
+  uint32_t inst, prim;
+};
+
+// Reciprocal for the slab tests only (MUFU.RCP, ~1 ulp): box tests are conservative by half a quantisation step
+// plus 2 ulp, results never depend on it.  The triangle test uses IEEE divisions (bit-exact with the oracle).
+ADEV float safe_rcp(float d) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fabsf(d) > 1e-20f ? d : copysignf(1e-20f, d)));
+  return r;
+}
+
+struct RaySpace {  // ray constants in the space being traversed (world or one instance's object space)
+  float3 o, idir;
+  float3 sx, sy, sz;  // watertight test: rows of the shear (e_kx - Sx e_kz, e_ky - Sy e_kz, Sz e_kz)
+  uint32_t oct;       // bit k set = direction negative on axis k
+};
+
+ADEV void setup_space(RaySpace& r, float3 o, float3 d) {
+  r.o = o;
+  r.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
+  r.oct = (r.idir.x < 0.f ? 1u : 0u) | (r.idir.y < 0.f ? 2u : 0u) | (r.idir.z < 0.f ? 4u : 0u);
+}
+// kz = dominant axis of d, kx = kz+1, ky = kz+2 (cyclic).  The kx/ky swap of the paper only flips the sign of
+// all three edge functions together (exactly, in floating point), which changes no result without culling.
+ADEV void setup_shear(RaySpace& r, float3 d) {
+  float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+  int kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+  float dz = comp(d, kz);
+  float dx = kz == 0 ? d.y : (kz == 1 ? d.z : d.x);
+  float dy = kz == 0 ? d.z : (kz == 1 ? d.x : d.y);
+  float Sx = dx / dz, Sy = dy / dz, Sz = 1.0f / dz;
+  if (kz == 0) r.sx = f3(-Sx, 1.f, 0.f), r.sy = f3(-Sy, 0.f, 1.f), r.sz = f3(Sz, 0.f, 0.f);
+  else if (kz == 1) r.sx = f3(0.f, -Sx, 1.f), r.sy = f3(1.f, -Sy, 0.f), r.sz = f3(0.f, Sz, 0.f);
+  else r.sx = f3(1.f, 0.f, -Sx), r.sy = f3(0.f, 1.f, -Sy), r.sz = f3(0.f, 0.f, Sz);
+}
+
+ADEV float dot_chain(float3 s, float3 a) { return __fmaf_rn(s.z, a.z, __fmaf_rn(s.y, a.y, __fmul_rn(s.x, a.x))); }
+
+// Watertight ray/triangle test, no culling.  Barycentrics in the Vulkan convention.
+ADEV bool hit_triangle(const RaySpace& r, float3 v0, float3 v1, float3 v2, float& t, float& b1, float& b2) {
+  float3 A = v0 - r.o, B = v1 - r.o, C = v2 - r.o;
+  float Ax = dot_chain(r.sx, A), Ay = dot_chain(r.sy, A);
+  float Bx = dot_chain(r.sx, B), By = dot_chain(r.sy, B);
+  float Cx = dot_chain(r.sx, C), Cy = dot_chain(r.sy, C);
+  // Edge functions with individually rounded products (no FMA contraction): the neighbour across a
+  // shared edge then computes the exact negative, which is what makes the test watertight.
+  float U = __fsub_rn(__fmul_rn(Cx, By), __fmul_rn(Cy, Bx));
+  float V = __fsub_rn(__fmul_rn(Ax, Cy), __fmul_rn(Ay, Cx));
+  float W = __fsub_rn(__fmul_rn(Bx, Ay), __fmul_rn(By, Ax));
+  if (U == 0.0f || V == 0.0f || W == 0.0f) {  // edge case: redo the edge functions in double
+    U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
+    V = (float)((double)Ax * (double)Cy - (double)Ay * (double)Cx);
+    W = (float)((double)Bx * (double)Ay - (double)By * (double)Ax);
+  }
+  if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
+  float det = __fadd_rn(__fadd_rn(U, V), W);
+  if (det == 0.0f) return false;
+  float Az = dot_chain(r.sz, A), Bz = dot_chain(r.sz, B), Cz = dot_chain(r.sz, C);
+  float T = __fadd_rn(__fadd_rn(__fmul_rn(U, Az), __fmul_rn(V, Bz)), __fmul_rn(W, Cz));
+  float inv = 1.0f / det;
+  t = T * inv;
+  b1 = V * inv;
+  b2 = W * inv;
+  return true;
+}
+
+// 0x4B000000 | byte = 2^23 + byte exactly: one PRMT turns a quantised plane into a float without the XU pipe.
+// `magic` must come from a register / the constant bank so that the selector stays an immediate.
+template <int J>
+ADEV float magic_byte(uint32_t v, uint32_t magic) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v), "r"(magic), "n"(0x7440 + J));
+  return __uint_as_float(d);
+}
+
+// Slab test of the eight quantised child boxes of one compressed wide node (Ylitie et al. 2017, section 3).
+// Plane t = q * a + b with a = 2^e / d, b = (p - o) / d; q arrives as 2^23 + q, so b is pre-biased by
+// -2^23 a, whose rounding error (<= |a| / 2, half a quantisation step) is covered by moving the near planes
+// half a step down and the far planes half a step up.  The far side is also widened by 2 ulp so that a box never
+// rejects what the watertight triangle test accepts.  Returns bit s = child in slot s hit.
+ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n2, uint4 n3, uint4 n4, const RaySpace& r, float tmin, float tmax,
+                                  uint32_t magic) {
+  const float kBias = 8388608.0f, kWiden = 1.0000004f;
+  const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * r.idir.x;
+  const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * r.idir.y;
+  const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * r.idir.z;
+  const float bx = fmaf(-kBias, ax, (__uint_as_float(n0.x) - r.o.x) * r.idir.x);
+  const float by = fmaf(-kBias, ay, (__uint_as_float(n0.y) - r.o.y) * r.idir.y);
+  const float bz = fmaf(-kBias, az, (__uint_as_float(n0.z) - r.o.z) * r.idir.z);
+  const float hx = 0.50001f * fabsf(ax), hy = 0.50001f * fabsf(ay), hz = 0.50001f * fabsf(az);
+  const float bnx = bx - hx, bny = by - hy, bnz = bz - hz;
+  const float afx = ax * kWiden, afy = ay * kWiden, afz = az * kWiden;
+  const float bfx = (bx + hx) * kWiden, bfy = (by + hy) * kWiden, bfz = (bz + hz) * kWiden;
+  const bool nx = (r.oct & 1u) != 0u, ny = (r.oct & 2u) != 0u, nz = (r.oct & 4u) != 0u;
+  uint32_t hit8 = 0;
+#pragma unroll
+  for (int h = 0; h < 2; h++) {
+    const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
+    const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
+    const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
+    const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
+    const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
+#define ASUNA_CHILD(J)                                                                                      \
+    {                                                                                                         \
+      float tnx = fmaf(magic_byte<J>(nearx, magic), ax, bnx), tfx = fmaf(magic_byte<J>(farx, magic), afx, bfx); \
+      float tny = fmaf(magic_byte<J>(neary, magic), ay, bny), tfy = fmaf(magic_byte<J>(fary, magic), afy, bfy); \
+      float tnz = fmaf(magic_byte<J>(nearz, magic), az, bnz), tfz = fmaf(magic_byte<J>(farz, magic), afz, bfz); \
+      float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                  \
+      float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                                  \
+      if (cmin <= cmax) hit8 |= 1u << (4 * h + J);                                                            \
+    }
+    ASUNA_CHILD(0) ASUNA_CHILD(1) ASUNA_CHILD(2) ASUNA_CHILD(3)
+#undef ASUNA_CHILD
+  }
+  return hit8;
+}
+
+// bit s -> bit (s ^ c): three conditional swaps of adjacent bits / pairs / nibbles
+ADEV uint32_t xor_permute8(uint32_t x, uint32_t c) {
+  if (c & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
+  if (c & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
+  if (c & 4u) x = ((x & 0x0Fu) << 4) | ((x >> 4) & 0x0Fu);
+  return x;
+}
+
+// Per-lane traversal state.  Stack entries are (base index, mask) groups: mask > 0x00FFFFFF = a node group
+// (hit bits of inner children in the top byte, already in visiting order: highest bit = nearest octant; imask in
+// the low byte), otherwise a primitive group (<= 24 hit bits of consecutive primitive slots).
+struct Lane {  // (the stack itself is a separate local array so that these stay in registers)
+  int sp, blas_sp;
+  uint2 ng, tg;
+  RaySpace rs;
+  float3 wo, wd;
+  float tmin, tmax;
+  HitRec best;
+  uint32_t cur_inst;
+  bool in_blas, found;
+  bool shear_ok;  // the watertight-test constants of the current instance are computed at its first triangle
+};
+
+ADEV void lane_begin(Lane& L, float3 o, float3 d, float tmin, float tmax) {
+  L.sp = 0, L.blas_sp = 0;
+  L.ng = make_uint2(0u, 0x80000000u);  // the instance-level root
+  L.tg = make_uint2(0u, 0u);
+  L.wo = o, L.wd = d, L.tmin = tmin, L.tmax = tmax;
+  setup_space(L.rs, o, d);
+  L.in_blas = false, L.found = false, L.shear_ok = false;
+  L.cur_inst = 0;
+  L.best.inst = 0xFFFFFFFFu, L.best.prim = 0xFFFFFFFFu, L.best.b1 = L.best.b2 = L.best.t = 0.f;
+}
+
+ADEV void lane_push(Lane& L, uint2* stack, uint2 e, uint32_t* overflow) {
+  if (L.sp < kStackSize) stack[L.sp++] = e;
+  else atomicAdd(overflow, 1u);
+}
+
+// One wide-node step: take the nearest pending child of the current node group, test its eight children.
+template <bool COUNT>
+ADEV void lane_node_step(Lane& L, uint2* stack, const SceneView& sc, uint32_t* overflow, uint32_t& n_nodes) {
+  const uint32_t hits = L.ng.y;
+  const uint32_t bit = 31u - (uint32_t)__clz(hits);
+  uint2 rest = make_uint2(L.ng.x, hits & ~(1u << bit));
+  const uint32_t octinv = 7u ^ L.rs.oct;
+  const uint32_t slot = (bit - 24u) ^ octinv;
+  const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+  const WideNode* nodes = L.in_blas ? sc.blas_nodes : sc.tlas_nodes;
+  const uint4* np = reinterpret_cast<const uint4*>(nodes + L.ng.x + rel);
+  const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+  if (COUNT) n_nodes++;
+  if (rest.y > 0x00FFFFFFu) lane_push(L, stack, rest, overflow);
+  const uint32_t hit8 = intersect_wide_node(n0, n2, n3, n4, L.rs, L.tmin, L.tmax, sc.magic);
+  const uint32_t imask = n0.w >> 24;
+  L.ng = make_uint2(n1.x, (xor_permute8(hit8 & imask, octinv) << 24) | imask);
+  uint32_t leaf = hit8 & ~imask, prims = 0;
+  while (leaf) {  // leaf children hit: their primitive bits (unary count << offset)
+    const uint32_t j = (uint32_t)__ffs((int)leaf) - 1u;
+    leaf &= leaf - 1u;
+    const uint32_t m = ((j & 4u) ? n1.w : n1.z) >> (8u * (j & 3u)) & 0xFFu;
+    prims |= (m >> 5) << (m & 31u);
+  }
+  if (prims) {
+    if (L.tg.y) lane_push(L, stack, L.tg, overflow);  // an older postponed group goes under the newer, nearer one
+    L.tg = make_uint2(n1.y, prims);
+  }
+}
+
+// Instance group at the top level: enter its first instance, keep the rest (and the pending node group) for later.
+ADEV void lane_enter_instance(Lane& L, uint2* stack, const SceneView& sc, uint32_t* overflow) {
+  const uint32_t k = (uint32_t)__ffs((int)L.tg.y) - 1u;
+  L.tg.y &= L.tg.y - 1u;
+  if (L.sp + 2 > kStackSize) {
+    atomicAdd(overflow, 1u);
+    L.tg.y = 0;
+    return;
+  }
+  if (L.tg.y) stack[L.sp++] = L.tg;
+  if (L.ng.y > 0x00FFFFFFu) stack[L.sp++] = L.ng;
+  L.cur_inst = __ldg(&sc.tlas_leaf_inst[L.tg.x + k]);
+  const DInstance* in = sc.instances + L.cur_inst;
+  float4 r0 = __ldg(&in->w2o[0]), r1 = __ldg(&in->w2o[1]), r2 = __ldg(&in->w2o[2]);
+  float4 m[3] = {r0, r1, r2};
+  setup_space(L.rs, xf_point(m, L.wo), xf_vector(m, L.wd));
+  L.shear_ok = false;
+  L.in_blas = true;
+  L.blas_sp = L.sp;
+  L.ng = make_uint2((uint32_t)__ldg(&in->blas_root), 0x80000000u);
+  L.tg = make_uint2(0u, 0u);
+}
+
+// One triangle of the current primitive group.  Returns true when the hit ends an any-hit query.
+template <bool ANY, bool COUNT>
+ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
+  const uint32_t k = (uint32_t)__ffs((int)L.tg.y) - 1u;
+  L.tg.y &= L.tg.y - 1u;
+  const TriSlot* tp = sc.tris + L.tg.x + k;
+  float4 v0 = __ldg(&tp->v0), v1 = __ldg(&tp->v1), v2 = __ldg(&tp->v2);
+  float t, b1, b2;
+  if (COUNT) n_tris++;
+  if (!L.shear_ok) {  // many instance visits never reach a triangle: the three IEEE divisions are paid only here
+    const DInstance* in = sc.instances + L.cur_inst;
+    float4 m[3] = {__ldg(&in->w2o[0]), __ldg(&in->w2o[1]), __ldg(&in->w2o[2])};
+    setup_shear(L.rs, xf_vector(m, L.wd));
+    L.shear_ok = true;
+  }
+  if (!hit_triangle(L.rs, f3(v0), f3(v1), f3(v2), t, b1, b2)) return false;
+  if (!(t > L.tmin)) return false;
+  uint32_t prim = __float_as_uint(v0.w);
+  bool closer = t < L.tmax || (t == L.tmax && L.found &&
+                               (L.cur_inst < L.best.inst || (L.cur_inst == L.best.inst && prim < L.best.prim)));
+  if (!closer) return false;
+  L.best.t = t, L.best.b1 = b1, L.best.b2 = b2, L.best.inst = L.cur_inst, L.best.prim = prim;
+  L.tmax = t;
+  L.found = true;
+  return ANY;
+}
+
+// Persistent warp loop.  Policy: load(i, o, d, tmin, tmax) reads ray i; commit(i, found, hit) stores its result.
+template <bool ANY, bool COUNT, class Policy>
+__device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t count, uint32_t* ticket, uint32_t* overflow,
+                                 unsigned long long* node_visits, unsigned long long* tri_tests) {
+  const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+  Lane L;
+  uint2 stack[kStackSize];
+  L.sp = 0, L.blas_sp = 0, L.in_blas = false, L.found = false, L.shear_ok = false;
+  L.ng = L.tg = make_uint2(0u, 0u);
+  bool active = false, exhausted = (count == 0) || sc.n_instances == 0;
+  uint32_t ray = 0, n_nodes = 0, n_tris = 0;
+  if (sc.n_instances == 0) {  // nothing to hit: every ray misses
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x); i < count; i += gridDim.x * blockDim.x) {
+      float3 o, d;
+      float t0, t1;
+      pol.load(i, o, d, t0, t1);
+      lane_begin(L, o, d, t0, t1);
+      pol.commit(i, false, L.best);
+    }
+    return;
+  }
+  for (;;) {
+    // ---- refill idle lanes from the queue: one atomic per warp
+    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+    if (!exhausted && idle) {
+      const uint32_t n_idle = __popc(idle), leader = (uint32_t)__ffs((int)idle) - 1u;
+      uint32_t base = 0;
+      if (lane == leader) base = atomicAdd(ticket, n_idle);
+      base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
+      if (!active) {
+        const uint32_t i = base + __popc(idle & lt);
+        if (i < count) {
+          float3 o, d;
+          float t0, t1;
+          pol.load(i, o, d, t0, t1);
+          lane_begin(L, o, d, t0, t1);
+          ray = i;
+          active = true;
+        }
+      }
+      if (base + n_idle >= count) exhausted = true;
+    }
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
+    // ---- traverse until enough lanes have finished to make a refill worthwhile
+    for (;;) {
+      // pop / leave instance / terminate; lanes holding only a postponed triangle group swap it under the next
+      // node group of their own mesh-level stack and keep traversing
+      if (active && L.ng.y <= 0x00FFFFFFu) {
+        if (L.tg.y == 0u) {
+          if (L.in_blas && L.sp == L.blas_sp) {
+            L.in_blas = false;
+            setup_space(L.rs, L.wo, L.wd);
+          }
+          if (L.sp == 0) {
+            pol.commit(ray, L.found, L.best);
+            active = false;
+          } else {
+            const uint2 e = stack[--L.sp];
+            if (e.y > 0x00FFFFFFu) L.ng = e;
+            else L.tg = e;
+          }
+        } else if (L.in_blas && L.sp > L.blas_sp && stack[L.sp - 1].y > 0x00FFFFFFu) {
+          const uint2 e = stack[L.sp - 1];
+          stack[L.sp - 1] = L.tg;
+          L.ng = e;
+          L.tg = make_uint2(0u, 0u);
+        }
+      }
+      if (active && L.ng.y > 0x00FFFFFFu) lane_node_step<COUNT>(L, stack, sc, overflow, n_nodes);
+      if (active && !L.in_blas && L.tg.y) lane_enter_instance(L, stack, sc, overflow);
+      const bool want_tri = active && L.in_blas && L.tg.y != 0u;
+      const uint32_t m_tri = __ballot_sync(0xFFFFFFFFu, want_tri);
+      const uint32_t m_node = __ballot_sync(0xFFFFFFFFu, active && L.ng.y > 0x00FFFFFFu);
+      const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, active);
+      if (m_tri && (m_node == 0u || __popc(m_tri) >= (__popc(m_act) >> sc.tri_vote_shift))) {
+        if (want_tri && lane_triangle_step<ANY, COUNT>(L, sc, n_tris)) {
+          pol.commit(ray, true, L.best);
+          active = false;
+        }
+      }
+      const uint32_t still = __ballot_sync(0xFFFFFFFFu, active);
+      if (still == 0u) break;
+      if (!exhausted && 32u - __popc(still) >= sc.refill_lanes) break;
+    }
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, o);
+      n_tris += __shfl_xor_sync(0xFFFFFFFFu, n_tris, o);
+    }
+    if (lane == 0) {
+      atomicAdd(node_visits, (unsigned long long)n_nodes);
+      atomicAdd(tri_tests, (unsigned long long)n_tris);
+    }
+  }
+}
+
+}  // namespace asuna

@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 METRIC = "1080p samples/sec"
 UNIT = "samples/s"
 WORKLOAD = "glass blob (dielectric + env-map), 1920x1080, depth 8 [BASELINE.json configs[1]]"
-NODE_BYTES, TRI_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 64, 48, 32, 16
+NODE_BYTES, TRI_BYTES, RAY_IN_BYTES, HIT_OUT_BYTES = 80, 48, 32, 16
 
 
 def build_scene(args):

@@ -151,30 +151,38 @@ inline bool hit_box(const Box& b, vec3 o, vec3 inv_d, float tmin, float tmax, fl
   return tn <= tf * 1.0000004f;
 }
 
-// Per-ray constants of the watertight test: dominant axis permutation and shear.
+// Per-ray constants of the watertight test: dominant axis kz, kx = kz+1, ky = kz+2 (cyclic), shear
+// Sx = d[kx]/d[kz], Sy = d[ky]/d[kz], Sz = 1/d[kz], kept as the three rows of the shear matrix
+// (e_kx - Sx e_kz, e_ky - Sy e_kz, Sz e_kz) so the test needs no permutation.  The kx/ky swap of the paper is
+// dropped: it negates all three edge functions together (exactly), which changes nothing without culling.
 struct RayShear {
-  int kx, ky, kz;
-  float Sx, Sy, Sz;
+  vec3 sx, sy, sz;
   explicit RayShear(vec3 d) {
     float ax = std::fabs(d.x), ay = std::fabs(d.y), az = std::fabs(d.z);
-    kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
-    kx = (kz + 1) % 3;
-    ky = (kx + 1) % 3;
-    if (d[kz] < 0.0f) std::swap(kx, ky);
-    Sx = d[kx] / d[kz];
-    Sy = d[ky] / d[kz];
-    Sz = 1.0f / d[kz];
+    int kz = (ax > ay) ? (ax > az ? 0 : 2) : (ay > az ? 1 : 2);
+    int kx = (kz + 1) % 3, ky = (kx + 1) % 3;
+    float Sx = d[kx] / d[kz], Sy = d[ky] / d[kz], Sz = 1.0f / d[kz];
+    float m[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+    m[0][kx] = 1.f, m[0][kz] = -Sx;
+    m[1][ky] = 1.f, m[1][kz] = -Sy;
+    m[2][kz] = Sz;
+    sx = vec3{m[0][0], m[0][1], m[0][2]};
+    sy = vec3{m[1][0], m[1][1], m[1][2]};
+    sz = vec3{m[2][0], m[2][1], m[2][2]};
   }
 };
+
+// fma(s.z, a.z, fma(s.y, a.y, s.x * a.x)): the exact operation order of the CUDA kernel (traverse.cuh dot_chain)
+inline float dot_chain(vec3 s, vec3 a) { return std::fmaf(s.z, a.z, std::fmaf(s.y, a.y, s.x * a.x)); }
 
 // Watertight ray/triangle test.  No back-face culling (the reference sets
 // VK_GEOMETRY_INSTANCE_TRIANGLE_FACING_CULL_DISABLE, src/pipeline/pipeline_raytrace.cpp:132).
 // Returns t and the Vulkan barycentrics (b1, b2): hit = (1-b1-b2) v0 + b1 v1 + b2 v2.
 inline bool hit_triangle(vec3 o, const RayShear& rs, vec3 v0, vec3 v1, vec3 v2, float& t, float& b1, float& b2) {
   vec3 A = v0 - o, B = v1 - o, C = v2 - o;
-  float Ax = A[rs.kx] - rs.Sx * A[rs.kz], Ay = A[rs.ky] - rs.Sy * A[rs.kz];
-  float Bx = B[rs.kx] - rs.Sx * B[rs.kz], By = B[rs.ky] - rs.Sy * B[rs.kz];
-  float Cx = C[rs.kx] - rs.Sx * C[rs.kz], Cy = C[rs.ky] - rs.Sy * C[rs.kz];
+  float Ax = dot_chain(rs.sx, A), Ay = dot_chain(rs.sy, A);
+  float Bx = dot_chain(rs.sx, B), By = dot_chain(rs.sy, B);
+  float Cx = dot_chain(rs.sx, C), Cy = dot_chain(rs.sy, C);
   float U = Cx * By - Cy * Bx, V = Ax * Cy - Ay * Cx, W = Bx * Ay - By * Ax;
   if (U == 0.0f || V == 0.0f || W == 0.0f) {
     U = (float)((double)Cx * (double)By - (double)Cy * (double)Bx);
@@ -184,7 +192,7 @@ inline bool hit_triangle(vec3 o, const RayShear& rs, vec3 v0, vec3 v1, vec3 v2, 
   if ((U < 0.0f || V < 0.0f || W < 0.0f) && (U > 0.0f || V > 0.0f || W > 0.0f)) return false;
   float det = U + V + W;
   if (det == 0.0f) return false;
-  float Az = rs.Sz * A[rs.kz], Bz = rs.Sz * B[rs.kz], Cz = rs.Sz * C[rs.kz];
+  float Az = dot_chain(rs.sz, A), Bz = dot_chain(rs.sz, B), Cz = dot_chain(rs.sz, C);
   float T = U * Az + V * Bz + W * Cz;
   float inv = 1.0f / det;
   t = T * inv;
