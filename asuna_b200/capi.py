@@ -14,7 +14,8 @@ import numpy as np
 from . import structs as S
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-PRODUCT_LIB = os.path.join(_HERE, "libasuna_b200.so")
+# ASUNA_B200_LIB: developer knob for A/B-ing kernel variants on the GPU box (same ABI, another build)
+PRODUCT_LIB = os.environ.get("ASUNA_B200_LIB") or os.path.join(_HERE, "libasuna_b200.so")
 
 # every symbol include/asuna_b200.h declares (tests check the .so exports all of them)
 ABI_SYMBOLS = (

@@ -84,14 +84,14 @@ struct UserPolicy {  // asuna_trace_rays / asuna_occlusion_rays / asuna_trace_pr
 };
 
 template <bool COUNT>
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, ASUNA_TRACE_MIN_BLOCKS)
 k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter, int qsel) {
   ClosestPolicy pol{ps, ps.queue[qsel], sc.instances};
   trace_persistent<false, COUNT>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow,
                                  &cnt->node_visits, &cnt->tri_tests);
 }
 
-__global__ void __launch_bounds__(kTraceThreads)
+__global__ void __launch_bounds__(kTraceThreads, ASUNA_TRACE_MIN_BLOCKS)
 k_trace_shadow(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter) {
   ShadowPolicy pol{ps};
   trace_persistent<true, false>(sc, pol, cnt->shadow[iter], &cnt->ticket_shadow[iter], &cnt->stack_overflow, nullptr,

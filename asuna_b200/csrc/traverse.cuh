@@ -21,6 +21,9 @@
 namespace asuna {
 
 constexpr int kTraceThreads = 128;
+#ifndef ASUNA_TRACE_MIN_BLOCKS
+#define ASUNA_TRACE_MIN_BLOCKS 6  // 80 registers: 24 resident warps per SM (measured best; 8 blocks spills)
+#endif
 constexpr int kStackSize = 40;        // uint2 entries: wide-BVH depth of the instance level + one mesh level
 
 struct HitRec {

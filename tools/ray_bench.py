@@ -13,6 +13,14 @@ frames = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 which = sys.argv[3] if len(sys.argv) > 3 else "rays"
 if which == "rays":
     sc = scenes.ray_bench(1920, 1080, subdiv=subdiv, depth=4)
+elif which == "rays_merged":  # same geometry as one mesh / one instance: what a flattened scene would cost
+    from asuna_b200 import host
+    import numpy as np
+    sc = scenes.ray_bench(1920, 1080, subdiv=subdiv, depth=4)
+    (v0, i0), (v1, i1) = sc.meshes[0], sc.meshes[1]
+    sc.meshes = [(np.concatenate([v0, v1]), np.concatenate([i0, i1 + len(v0)]))]
+    sc.mesh_ids = {"blob": 0}
+    sc.instances = sc.instances[:1]
 elif which == "glass":
     sc = scenes.glass_blob(1920, 1080, subdiv=subdiv, env_size=(2048, 1024))
 else:
