@@ -212,7 +212,8 @@ def envmap_tables(rgba):
     """reference src/core/texture.cpp:144-226.  Returns (marginal, conditional) RGBA32F tables."""
     img = np.ascontiguousarray(rgba, f32)
     h, w = img.shape[:2]
-    weight = (0.3 * img[..., 0].astype(np.float64) + 0.6 * img[..., 1] + 0.1 * img[..., 2]).astype(f32)
+    weight = (0.3 * img[..., 0].astype(np.float64) + 0.6 * img[..., 1].astype(np.float64)
+              + 0.1 * img[..., 2].astype(np.float64)).astype(f32)  # double arithmetic, texture.cpp:167
     cdf2d = np.cumsum(weight, axis=1, dtype=f32)            # sequential fp32 row prefix sums
     row_sum = cdf2d[:, -1].copy()
     denom = row_sum.astype(np.float64) + 1e-7
