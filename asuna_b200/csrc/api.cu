@@ -238,19 +238,7 @@ void make_instance_matrices(const float x[16], DInstance& d) {
   }
 }
 
-bool in_scope(uint32_t type) {
-  switch (type) {
-    case ASUNA_MAT_LAMBERTIAN:
-    case ASUNA_MAT_KANG18:
-    case ASUNA_MAT_EMISSIVE:
-    case ASUNA_MAT_PBR_METALNESS_ROUGHNESS:
-    case ASUNA_MAT_PLASTIC:
-    case ASUNA_MAT_ROUGH_PLASTIC:
-    case ASUNA_MAT_CONDUCTOR:
-    case ASUNA_MAT_DIELECTRIC: return true;
-    default: return false;
-  }
-}
+bool in_scope(uint32_t type) { return type < ASUNA_MAT_NUM; }  // all twelve closest-hit shaders of the reference
 
 FrameParams make_frame_params(asuna_ctx* ctx) {
   FrameParams fp{};
@@ -420,7 +408,7 @@ int asuna_add_mesh(asuna_ctx* ctx, const AsunaVertex* v, uint32_t nv, const uint
 
 int asuna_add_material(asuna_ctx* ctx, const AsunaMaterial* m) {
   if (!m) return fail(ctx, ASUNA_E_INVALID, "null material");
-  if (!in_scope(m->type)) return fail(ctx, ASUNA_E_UNSUPPORTED, "material type outside the hot-path scope (SURVEY.md 8f)");
+  if (!in_scope(m->type)) return fail(ctx, ASUNA_E_UNSUPPORTED, "unknown material type");
   ctx->materials.push_back(*m);
   ctx->scene_dirty = true;
   return (int)ctx->materials.size() - 1;
@@ -583,7 +571,8 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   ctx->may_pass_through = false;
   for (auto& m : ctx->materials)
     if ((m.type == ASUNA_MAT_PBR_METALNESS_ROUGHNESS && (m.opacityTextureId >= 0 || m.specular > 0.f)) ||
-        (m.type == ASUNA_MAT_KANG18 && (m.opacityTextureId >= 0 || m.metalness > 0.f)))
+        (m.type == ASUNA_MAT_KANG18 && (m.opacityTextureId >= 0 || m.metalness > 0.f)) ||
+        (m.type == ASUNA_MAT_DISNEY && (m.opacityTextureId >= 0 || m.rhoSpec[0] > 0.f)))
       ctx->may_pass_through = true;
   ctx->scene_dirty = false;
   return 0;

@@ -312,6 +312,10 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
           else if constexpr (T == ASUNA_MAT_ROUGH_PLASTIC) shade_rough_plastic(se, p, s, m);
           else if constexpr (T == ASUNA_MAT_PBR_METALNESS_ROUGHNESS) shade_pbr(se, p, s, m, pixel);
           else if constexpr (T == ASUNA_MAT_KANG18) shade_kang18(se, p, s, m, in, pixel);
+          else if constexpr (T == ASUNA_MAT_MIRROR) shade_mirror(se, p, s, m);
+          else if constexpr (T == ASUNA_MAT_ROUGH_CONDUCTOR) shade_rough_conductor(se, p, s, m);
+          else if constexpr (T == ASUNA_MAT_PHONG) shade_phong(se, p, s, m, pixel);
+          else if constexpr (T == ASUNA_MAT_DISNEY) shade_disney(se, p, s, m);
           else p.stop = true;
         }
       }

@@ -986,6 +986,362 @@ ADEV void shade_kang18(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaM
   two_lobe_sample(se, p, s, diffuse_term, f3(F0), ks, ax, ay, p_diffuse, false);
 }
 
+// ---- brdf_mirror.rchit:39-101 ------------------------------------------------------------------
+ADEV void shade_mirror(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m) {
+  float3 kd = diffuse_of(se, m, s);
+  apply_normal_map(se, m, s);
+  sample_lights_rng_only(se, p);  // eval(:12-19) is called with EArea and tests EDelta: identically 0
+  float3 d = reflect(-s.V, s.ffN);  // sampleBsdf(:28-37): no random numbers, pdf 1
+  if (length(kd) == 0.0f) {
+    p.stop = true;
+    return;
+  }
+  p.bsdf_pdf = 1.0f;
+  p.bsdf_flags = kSpecularReflection;
+  p.ray_o = offset_position_along_normal(s.pos, s.ffN);
+  p.ray_d = d;
+  p.throughput *= kd;  // divides by pdf (= 1), not pdf + EPS
+}
+
+// ---- brdf_rough_conductor.rchit -----------------------------------------------------------------
+ADEV float3 conductor_reflectance3(float3 eta, float3 k, float c) {
+  return f3(conductor_reflectance(eta.x, k.x, c), conductor_reflectance(eta.y, k.y, c), conductor_reflectance(eta.z, k.z, c));
+}
+ADEV float3 rough_conductor_term(float3 L, const Surface& s, float3 kd, float3 eta, float3 k, float ax, float ay, float NdotL,
+                                 float NdotV) {  // :86-95 == :136-146
+  const float3 N = s.ffN, V = s.V;
+  float3 H = make_normal(L + V);
+  float3 Fs = conductor_reflectance3(eta, k, NdotL);
+  float Gs = ggx_g1(NdotV, dot(V, s.X), dot(V, s.Y), ax, ay);
+  Gs *= ggx_g1(NdotL, dot(L, s.X), dot(L, s.Y), ax, ay);
+  float Ds = ggx_d(dot(H, N), dot(H, s.X), dot(H, s.Y), ax, ay);
+  return kd * Fs * Gs * Ds * NdotL;
+}
+ADEV void shade_rough_conductor(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m) {  // :151-220
+  float3 kd = diffuse_of(se, m, s);
+  float2 alpha = make_float2(m.anisoAlpha[0], m.anisoAlpha[1]);
+  if (m.roughnessTextureId >= 0) {
+    float4 c = tex(se, m.roughnessTextureId, s.uv);
+    alpha = make_float2(c.x, c.y);
+  }
+  apply_normal_map(se, m, s);
+  float3 eta = f3(m.radiance), k = f3(m.radianceFactor);
+  float ax = fmaxf(alpha.x, kEps), ay = fmaxf(alpha.y, kEps);
+  const float3 N = s.ffN, V = s.V;
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float3 w = f3(0.0f);
+    float bpdf = 0.0f;
+    if (visible) {
+      float NdotL = dot(ls.d, N), NdotV = dot(V, N);
+      if (!(NdotL < 0 || NdotV < 0)) {
+        w = rough_conductor_term(ls.d, s, kd, eta, k, ax, ay, NdotL, NdotV);
+        if (ls.flags & kLightArea) {
+          float3 wi = to_local(s.X, s.Y, N, ls.d), wo = to_local(s.X, s.Y, N, V);
+          bpdf = ggx_pdf(make_normal(wi + wo), wo, ax, ay);
+        }
+      }
+    }
+    store_direct(p, visible, w, bpdf, radiance, ls);
+  }
+  float2 u = rnd2(p.seed);
+  float NdotV = dot(V, N);
+  if (NdotV <= 0) {
+    p.stop = true;
+    return;
+  }
+  float3 wo = to_local(s.X, s.Y, N, V);
+  float3 wi = ggx_sample(u, wo, ax, ay);
+  float3 L = to_world(s.X, s.Y, N, wi);
+  float3 wh = make_normal(wi + wo);
+  float NdotL = dot(N, L);
+  float3 w = rough_conductor_term(L, s, kd, eta, k, ax, ay, NdotL, NdotV);
+  next_ray(p, s, L, ggx_pdf(wh, wo, ax, ay), kGlossyReflection, w, s.ffN);
+}
+
+// ---- brdf_phong.rchit -----------------------------------------------------------------------------
+ADEV float3 glsl_normalize(float3 v) { return v / length(v); }  // GLSL normalize: no zero-length guard
+ADEV float3 phong_eval(float3 L, float3 V, float3 N, float3 diffuse, float3 specular, float shininess, float dw) {  // :12-31, EArea
+  float NdotL = dot(N, L), NdotV = dot(N, V);
+  if (NdotL < 0 || NdotV < 0) return f3(0.0f);
+  float3 H = glsl_normalize(L + V);
+  float3 diffuse_lobe = diffuse * kInvPi;
+  float3 specular_lobe = specular * powf(fmaxf(dot(H, N), 0.0f), shininess) * (shininess + 2) * kInv2Pi;
+  return (dw * diffuse_lobe + (1 - dw) * specular_lobe) * NdotL;
+}
+ADEV float phong_pdf(float3 L, float3 V, float3 N, float shininess) {  // :33-38
+  float3 H = glsl_normalize(L + V);
+  float NdotH = fmaxf(dot(H, N), 0.0f), VdotH = fmaxf(dot(H, V), 0.0f);
+  return (shininess + 1) * kInv2Pi * powf(NdotH, shininess) * 0.25f / (VdotH + kEps);
+}
+ADEV void shade_phong(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& m, uint32_t pixel) {  // :113-193
+  const AsunaState& pc = se.fp->pc;
+  float3 diffuse = diffuse_of(se, m, s);
+  apply_normal_map(se, m, s);
+  float3 specular = f3(m.rhoSpec);
+  float shininess = m.specular;
+  if (p.depth == 1) {
+    write_aov(se, pixel, pc.diffuseOutChannel, diffuse);
+    write_aov(se, pixel, pc.normalOutChannel, s.ffN);
+    write_aov(se, pixel, pc.specularOutChannel, specular);
+    write_aov(se, pixel, pc.tangentOutChannel, s.X);
+    write_aov(se, pixel, pc.roughnessOutChannel, f3(1, 1, 0));
+    write_aov(se, pixel, pc.positionOutChannel, s.pos);
+    write_aov(se, pixel, pc.uvOutChannel, f3(s.uv.x, s.uv.y, 1));
+  }
+  const float3 N = s.ffN, V = s.V;
+  float db = luminance(diffuse), sb = luminance(specular);
+  float dw = db / (db + sb), sw = 1 - dw;
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float3 w = f3(0.0f);
+    float bpdf = 0.0f;
+    if (visible) {
+      w = phong_eval(ls.d, V, N, diffuse, specular, shininess, dw);
+      if (ls.flags & kLightArea) bpdf = dw * cosine_hemisphere_pdf(dot(N, ls.d)) + sw * phong_pdf(ls.d, V, N, shininess);
+    }
+    store_direct(p, visible, w, bpdf, radiance, ls);
+  }
+  float2 u = rnd2(p.seed);
+  float3 d;
+  float pdf;
+  uint32_t flags;
+  if (u.x < dw) {
+    u.x /= dw;
+    float3 wi = cosine_sample_hemisphere(u);
+    pdf = cosine_hemisphere_pdf(wi.z);
+    d = to_world(s.X, s.Y, N, wi);
+    flags = kDiffuseReflection;
+  } else {
+    u.x = (u.x - dw) / sw;
+    float ct = powf(u.x, 1 / (shininess + 1));
+    float phi = kTwoPi * u.y;
+    float st = safe_sqrt(1 - ct * ct);
+    float3 H = to_world(s.X, s.Y, N, f3(st * sinf(phi), st * cosf(phi), ct));
+    d = reflect(-V, H);
+    pdf = phong_pdf(d, V, N, shininess);
+    flags = kGlossyReflection;
+  }
+  float3 w = phong_eval(d, V, N, diffuse, specular, shininess, dw);
+  if (pdf <= 0.0f || length(w) == 0.0f) {
+    p.stop = true;
+    return;
+  }
+  p.bsdf_pdf = pdf;
+  p.bsdf_flags = flags;
+  p.ray_o = offset_position_along_normal(s.pos, s.ffN);
+  p.ray_d = d;
+  p.throughput *= w / pdf;
+}
+
+// ---- brdf_disney.rchit ------------------------------------------------------------------------------
+struct DisneyMat {  // :31-49 (the fields the shader reads)
+  float3 base;
+  float metallic, roughness, subsurface, specular_tint, sheen, sheen_tint, clearcoat, clearcoat_roughness, ax, ay;
+};
+ADEV float lum709(float3 c) { return 0.212671f * c.x + 0.715160f * c.y + 0.072169f * c.z; }  // :51-53
+ADEV float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+ADEV float gtr1(float NdotH, float a) {  // :55-60
+  if (a >= 1.0f) return kInvPi;
+  float a2 = a * a;
+  float t = 1.0f + (a2 - 1.0f) * NdotH * NdotH;
+  return (a2 - 1.0f) / (kPi * logf(a2) * t);
+}
+ADEV float3 sample_gtr1(float rgh, float r1) {  // :62-74
+  float a = fmaxf(0.001f, rgh);
+  float a2 = a * a;
+  float phi = r1 * kTwoPi;
+  float ct = sqrtf((1.0f - powf(a2, 1.0f - r1)) / (1.0f - a2));
+  float st = clampf(sqrtf(1.0f - (ct * ct)), 0.0f, 1.0f);
+  return f3(st * cosf(phi), st * sinf(phi), ct);
+}
+ADEV float3 sample_ggx_vndf(float3 V, float ax, float ay, float r1, float r2) {  // :96-114
+  float3 Vh = glsl_normalize(f3(ax * V.x, ay * V.y, V.z));
+  float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+  float3 T1 = lensq > 0 ? f3(-Vh.y, Vh.x, 0) * (1.0f / sqrtf(lensq)) : f3(1, 0, 0);
+  float3 T2 = cross(Vh, T1);
+  float r = sqrtf(r1);
+  float phi = 2.0f * kPi * r2;
+  float t1 = r * cosf(phi), t2 = r * sinf(phi);
+  float sv = 0.5f * (1.0f + Vh.z);
+  t2 = (1.0f - sv) * sqrtf(1.0f - t1 * t1) + sv * t2;
+  float3 Nh = t1 * T1 + t2 * T2 + sqrtf(fmaxf(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
+  return glsl_normalize(f3(ax * Nh.x, ay * Nh.y, fmaxf(0.0f, Nh.z)));
+}
+ADEV float gtr2_aniso(float NdotH, float HdotX, float HdotY, float ax, float ay) {  // :116-121
+  float a = HdotX / ax, b = HdotY / ay;
+  float c = a * a + b * b + NdotH * NdotH;
+  return 1.0f / (kPi * ax * ay * c * c);
+}
+ADEV float smith_g(float NdotV, float alpha_g) {  // :134-138
+  float a = alpha_g * alpha_g, b = NdotV * NdotV;
+  return (2.0f * NdotV) / (NdotV + sqrtf(a + b - a * b));
+}
+ADEV float smith_g_aniso(float NdotV, float VdotX, float VdotY, float ax, float ay) {  // :140-145
+  float a = VdotX * ax, b = VdotY * ay, c = NdotV;
+  return (2.0f * NdotV) / (NdotV + sqrtf(a * a + b * b + c * c));
+}
+ADEV float schlick_fresnel(float u) {  // :147-151
+  float m = clampf(1.0f - u, 0.0f, 1.0f);
+  float m2 = m * m;
+  return m2 * m2 * m;
+}
+ADEV float disney_fresnel(float metallic, float eta, float LdotH, float VdotH) {  // :167-171
+  return mixf(dielectric_fresnel(fabsf(VdotH), eta), schlick_fresnel(LdotH), metallic);
+}
+ADEV float3 disney_diffuse(const DisneyMat& m, float3 Csheen, float3 V, float3 L, float3 H, float& pdf) {  // :173-197
+  pdf = 0.0f;
+  if (L.z <= 0.0f) return f3(0.0f);
+  float FL = schlick_fresnel(L.z), FV = schlick_fresnel(V.z), FH = schlick_fresnel(dot(L, H));
+  float Fd90 = 0.5f + 2.0f * dot(L, H) * dot(L, H) * m.roughness;
+  float Fd = mixf(1.0f, Fd90, FL) * mixf(1.0f, Fd90, FV);
+  float Fss90 = dot(L, H) * dot(L, H) * m.roughness;
+  float Fss = mixf(1.0f, Fss90, FL) * mixf(1.0f, Fss90, FV);
+  float ss = 1.25f * (Fss * (1.0f / (L.z + V.z) - 0.5f) + 0.5f);
+  float3 Fsheen = FH * m.sheen * Csheen;
+  pdf = L.z * kInvPi;
+  return (1.0f - m.metallic) * (kInvPi * mixf(Fd, ss, m.subsurface) * m.base + Fsheen);
+}
+ADEV float3 disney_spec(const DisneyMat& m, float eta, float3 spec_col, float3 V, float3 L, float3 H, float& pdf) {  // :199-212
+  pdf = 0.0f;
+  if (L.z <= 0.0f) return f3(0.0f);
+  float FM = disney_fresnel(m.metallic, eta, dot(L, H), dot(V, H));
+  float3 F = mix3(spec_col, f3(1.0f), FM);
+  float D = gtr2_aniso(H.z, H.x, H.y, m.ax, m.ay);
+  float G1 = smith_g_aniso(fabsf(V.z), V.x, V.y, m.ax, m.ay);
+  float G2 = G1 * smith_g_aniso(fabsf(L.z), L.x, L.y, m.ax, m.ay);
+  pdf = G1 * D / (4.0f * V.z);
+  return F * D * G2 / (4.0f * L.z * V.z);
+}
+ADEV float3 disney_clearcoat(const DisneyMat& m, float3 V, float3 L, float3 H, float& pdf) {  // :214-226
+  pdf = 0.0f;
+  if (L.z <= 0.0f) return f3(0.0f);
+  float FH = dielectric_fresnel(dot(V, H), 1.0f / 1.5f);
+  float F = mixf(0.04f, 1.0f, FH);
+  float D = gtr1(H.z, m.clearcoat_roughness);
+  float G = smith_g(L.z, 0.25f) * smith_g(V.z, 0.25f);
+  float jacobian = 1.0f / (4.0f * dot(V, H));
+  pdf = D * H.z * jacobian;
+  return f3(0.25f) * m.clearcoat * F * D * G / (4.0f * L.z * V.z);
+}
+ADEV void disney_spec_color(const DisneyMat& m, float eta, float3& spec_col, float3& sheen_col) {  // :228-236
+  float lum = lum709(m.base);
+  float3 ctint = lum > 0.0f ? m.base / lum : f3(1.0f);
+  float F0 = (1.0f - eta) / (1.0f + eta);
+  spec_col = mix3(F0 * F0 * mix3(f3(1.0f), ctint, m.specular_tint), m.base, m.metallic);
+  sheen_col = mix3(f3(1.0f), ctint, m.sheen_tint);
+}
+ADEV void disney_lobes(const DisneyMat& m, float3 spec_col, float approx_fresnel, float& wd, float& ws, float& wc) {  // :238-250
+  wd = lum709(m.base) * (1.0f - m.metallic);
+  ws = lum709(mix3(spec_col, f3(1.0f), approx_fresnel));
+  wc = 0.25f * m.clearcoat * (1.0f - m.metallic);
+  float total = wd + ws + wc;
+  wd /= total, ws /= total, wc /= total;
+}
+ADEV float3 disney_eval(float3 Lw, const Surface& s, const DisneyMat& m, float eta, float& bsdf_pdf) {  // :252-300, EArea
+  float3 weight = f3(0.0f);
+  bsdf_pdf = 0.0f;
+  float3 V = to_local(s.X, s.Y, s.ffN, s.V), L = to_local(s.X, s.Y, s.ffN, Lw);
+  if (L.z <= 0 || V.z <= 0) return weight;
+  float3 H = glsl_normalize(L + V);
+  if (H.z < 0.0f) H = -H;
+  float3 spec_col, sheen_col;
+  disney_spec_color(m, eta, spec_col, sheen_col);
+  float wd, ws, wc;
+  disney_lobes(m, spec_col, disney_fresnel(m.metallic, eta, dot(L, H), dot(V, H)), wd, ws, wc);
+  float pdf = 0.0f;
+  if (wd > 0.0f) {
+    weight += disney_diffuse(m, sheen_col, V, L, H, pdf);
+    bsdf_pdf += pdf * wd;
+  }
+  if (ws > 0.0f) {
+    weight += disney_spec(m, eta, spec_col, V, L, H, pdf);
+    bsdf_pdf += pdf * ws;
+  }
+  if (wc > 0.0f) {
+    weight += disney_clearcoat(m, V, L, H, pdf);
+    bsdf_pdf += pdf * wc;
+  }
+  return weight * L.z;
+}
+ADEV void shade_disney(const ShadeEnv& se, PathRegs& p, Surface& s, const AsunaMaterial& mt) {  // :373-487
+  float3 base = diffuse_of(se, mt, s);
+  float metalness = mt.metalnessTextureId >= 0 ? tex(se, mt.metalnessTextureId, s.uv).x : mt.metalness;
+  float roughness = mt.roughnessTextureId >= 0 ? tex(se, mt.roughnessTextureId, s.uv).x : mt.roughness;
+  apply_normal_map(se, mt, s);
+  float opacity = mt.opacityTextureId >= 0 ? tex(se, mt.opacityTextureId, s.uv).x : mt.rhoSpec[0];
+  if (pass_through(p, s, opacity)) return;
+  DisneyMat m;
+  float aspect = sqrtf(1.0f - mt.anisotropic * 0.9f);
+  m.ax = fmaxf(0.001f, roughness * roughness / aspect);
+  m.ay = fmaxf(0.001f, roughness * roughness * aspect);
+  m.base = base;
+  m.metallic = metalness;
+  m.roughness = fmaxf(roughness * roughness, 0.001f);
+  m.subsurface = mt.subsurface, m.specular_tint = mt.specularTint, m.sheen = mt.sheen, m.sheen_tint = mt.sheenTint;
+  m.clearcoat = mt.clearcoat;
+  m.clearcoat_roughness = mixf(0.1f, 0.001f, mt.clearcoatGloss);
+  float eta = dot(s.V, s.N) > 0.0f ? (1.0f / mt.ior) : mt.ior;
+  {
+    bool visible;
+    LightSample ls;
+    float3 radiance = sample_lights(se, p, s.pos, s.ffN, visible, ls);
+    float3 w = f3(0.0f);
+    float bpdf = 0.0f;
+    if (visible) w = disney_eval(ls.d, s, m, eta, bpdf);
+    store_direct(p, visible, w, bpdf, radiance, ls);
+  }
+  float2 u = rnd2(p.seed);  // sampleBsdf(:302-371)
+  float r1 = u.x, r2 = u.y, pdf = 0.0f;
+  float3 f = f3(0.0f), L;
+  uint32_t flags;
+  const float3 N = s.ffN;
+  float3 V = to_local(s.X, s.Y, N, s.V);
+  float3 spec_col, sheen_col;
+  disney_spec_color(m, eta, spec_col, sheen_col);
+  float wd, ws, wc;
+  disney_lobes(m, spec_col, disney_fresnel(m.metallic, eta, V.z, V.z), wd, ws, wc);
+  float cdf0 = wd, cdf1 = cdf0 + wc;
+  if (r1 < cdf0) {
+    r1 /= cdf0;
+    L = cosine_sample_hemisphere(make_float2(r1, r2));
+    f = disney_diffuse(m, sheen_col, V, L, glsl_normalize(L + V), pdf);
+    pdf *= wd;
+    flags = kDiffuseReflection;
+  } else if (r1 < cdf1) {
+    r1 = (r1 - cdf0) / (cdf1 - cdf0);
+    float3 H = sample_gtr1(m.clearcoat_roughness, r1);
+    if (H.z < 0.0f) H = -H;
+    L = glsl_normalize(reflect(-V, H));
+    f = disney_clearcoat(m, V, L, H, pdf);
+    pdf *= wc;
+    flags = kGlossyReflection;
+  } else {
+    r1 = (r1 - cdf1) / (1.0f - cdf1);
+    float3 H = sample_ggx_vndf(V, m.ax, m.ay, r1, r2);
+    if (H.z < 0.0f) H = -H;
+    L = glsl_normalize(reflect(-V, H));
+    f = disney_spec(m, eta, spec_col, V, L, H, pdf);
+    pdf *= ws;
+    flags = kGlossyReflection;
+  }
+  float3 d = to_world(s.X, s.Y, N, L);
+  float3 w = f * fabsf(dot(N, L));  // :370 mixes the world-space normal with the local direction, as written
+  if (pdf <= 0.0f || length(w) == 0.0f) {
+    p.stop = true;
+    return;
+  }
+  p.bsdf_pdf = pdf;
+  p.bsdf_flags = flags;
+  p.ray_o = offset_position_along_normal(s.pos, s.ffN);
+  p.ray_d = d;
+  p.throughput *= w / pdf;
+}
+
 // ---- miss: raytrace.default.rmiss:24-55 -------------------------------------------------------
 ADEV void shade_miss(const ShadeEnv& se, PathRegs& p) {
   const AsunaState& pc = se.fp->pc;

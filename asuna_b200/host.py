@@ -203,8 +203,7 @@ _MATERIAL_TYPES = {
     "brdf_rough_plastic": S.MAT_ROUGH_PLASTIC, "brdf_conductor": S.MAT_CONDUCTOR,
     "brdf_mirror": S.MAT_MIRROR, "brdf_rough_conductor": S.MAT_ROUGH_CONDUCTOR, "brdf_disney": S.MAT_DISNEY,
     "brdf_phong": S.MAT_PHONG}
-IN_SCOPE_MATERIALS = (S.MAT_LAMBERTIAN, S.MAT_PBR, S.MAT_EMISSIVE, S.MAT_KANG18, S.MAT_DIELECTRIC, S.MAT_PLASTIC,
-                      S.MAT_ROUGH_PLASTIC, S.MAT_CONDUCTOR)
+IN_SCOPE_MATERIALS = tuple(range(12))  # all twelve closest-hit shaders of the reference (src/shared/material.h:7-21)
 
 
 # ----------------------------------------------------------------------------- env map

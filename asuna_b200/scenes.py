@@ -289,6 +289,28 @@ def cornell_materials(width=256, height=256, spp=16, depth=5, env=False, lights=
     return sc
 
 
+def cornell_all_materials(width=256, height=256, spp=16, depth=5, env=False, lights="rect", textured=False, seed=3):
+    """cornell_materials plus the four remaining closest-hit shaders of the reference (mirror, rough_conductor,
+    phong, disney -- SURVEY.md 8f row 1): all twelve material types in one frame."""
+    sc = cornell_materials(width, height, spp, depth, env, lights, textured, seed)
+    from .host import COMPLEX_IOR
+    t = lambda k: sc.texture_ids.get(k, -1)
+    sc.add_material("mirror", mat(S.MAT_MIRROR, diffuse=(.9, .92, .95)))
+    sc.add_material("copper", mat(S.MAT_ROUGH_CONDUCTOR, diffuse=(1, 1, 1), radiance=COMPLEX_IOR["Cu"][0],
+                                  radianceFactor=COMPLEX_IOR["Cu"][1], anisoAlpha=(0.25, 0.1), roughnessTextureId=-1))
+    sc.add_material("phong", mat(S.MAT_PHONG, diffuse=(.2, .3, .7), rhoSpec=(.6, .6, .5), specular=40.0,
+                                 diffuseTextureId=t("albedo")))
+    sc.add_material("disney", mat(S.MAT_DISNEY, diffuse=(.7, .25, .2), metalness=0.3, roughness=0.4, subsurface=0.2,
+                                  specularTint=0.3, anisotropic=0.5, sheen=0.4, sheenTint=0.6, clearcoat=0.8,
+                                  clearcoatGloss=0.7, ior=1.45, normalTextureId=t("normal"), opacityTextureId=t("opacity")))
+    sc.materials[-1]["rhoSpec"][0] = 0.0 if textured else 0.15  # disney keeps its opacity constant in rhoSpec.x
+    sc.add_instance("ball", "mirror", translation((0.22, 0.72, 0.32)) @ scaling((0.1, 0.1, 0.1)))
+    sc.add_instance("ball", "copper", translation((0.45, 0.12, 0.78)) @ scaling((0.11, 0.11, 0.11)))
+    sc.add_instance("unit_box", "phong", translation((0.82, 0.3, 0.25)) @ rotation_y(math.radians(30)) @ scaling((0.16, 0.22, 0.16)))
+    sc.add_instance("ball", "disney", translation((0.5, 0.38, 0.45)) @ scaling((0.12, 0.12, 0.12)))
+    return sc
+
+
 _FDR_CACHE = {}
 
 

@@ -629,6 +629,391 @@ struct oracle_ctx {
     nextRay(p, s, bRec, weight, s.ffN);
   }
 
+  // ------------------------------------------------------------------ brdf_mirror.rchit:39-101
+  void chitMirror(RayPayload& p, HitState& s) const {
+    fetchDiffuse(s);
+    applyNormalMap(s);
+    vec3 kd(s.mat.diffuse);
+    {
+      bool visible;
+      LightSamplingRecord lRec;
+      vec3 radiance = sampleLights(p, p.pRec.ray.d, s.pos, s.ffN, visible, lRec);
+      vec3 w(0.0f);  // eval(:12-19) is called with EArea: the EDelta test fails -> 0
+      float bsdfPdf = 0.0f;
+      if (visible && (lRec.flags & EDelta) != 0)  // pdf(:21-26) with lRec.flags
+        if (std::fabs(dot(reflect(-s.V, s.ffN), lRec.d) - 1) < EPS) bsdfPdf = 1.0f;
+      storeDirect(p, visible, w, bsdfPdf, radiance, lRec);
+    }
+    BsdfSamplingRecord bRec;  // sampleBsdf(:28-37): no random numbers
+    bRec.pdf = 1.0f;
+    bRec.d = reflect(-s.V, s.ffN);
+    bRec.flags = ESpecularReflection;
+    vec3 bsdfWeight = kd;
+    if (bRec.pdf <= 0.0f || isBlack(bsdfWeight)) {
+      p.pRec.stop = true;
+      return;
+    }
+    p.bRec = bRec;
+    p.pRec.ray = Ray{offsetPositionAlongNormal(s.pos, s.ffN), bRec.d};
+    p.pRec.throughput *= bsdfWeight / bRec.pdf;
+  }
+
+  // ------------------------------------------------------------------ brdf_rough_conductor.rchit
+  vec3 roughConductorEval(vec3 L, vec3 V, vec3 N, vec3 X, vec3 Y, vec3 kd, vec3 eta, vec3 k, float ax, float ay) const {  // :79-98, EArea
+    float NdotL = dot(L, N), NdotV = dot(V, N);
+    if (NdotL < 0 || NdotV < 0) return vec3(0.0f);
+    vec3 H = makeNormal(L + V);
+    vec3 Fs = conductorReflectance3(eta, k, NdotL);
+    float Gs = g1SmithAnisoGGX(NdotV, dot(V, X), dot(V, Y), ax, ay);
+    Gs *= g1SmithAnisoGGX(NdotL, dot(L, X), dot(L, Y), ax, ay);
+    float Ds = dAnisoGGX(dot(H, N), dot(H, X), dot(H, Y), ax, ay);
+    return kd * Fs * Gs * Ds * NdotL;
+  }
+  void chitRoughConductor(RayPayload& p, HitState& s) const {  // :151-220
+    fetchDiffuse(s);
+    if (s.mat.roughnessTextureId >= 0) {
+      vec4 c = textureEval(s.mat.roughnessTextureId, s.uv);
+      s.mat.anisoAlpha[0] = c.x, s.mat.anisoAlpha[1] = c.y;
+    }
+    applyNormalMap(s);
+    vec3 kd(s.mat.diffuse), eta(s.mat.radiance), k(s.mat.radianceFactor);
+    float ax = std::fmax(s.mat.anisoAlpha[0], EPS), ay = std::fmax(s.mat.anisoAlpha[1], EPS);
+    const vec3 N = s.ffN, V = s.V, X = s.X, Y = s.Y;
+    {
+      bool visible;
+      LightSamplingRecord lRec;
+      vec3 radiance = sampleLights(p, p.pRec.ray.d, s.pos, s.ffN, visible, lRec);
+      vec3 w(0.0f);
+      float bsdfPdf = 0.0f;
+      if (visible) {
+        w = roughConductorEval(lRec.d, V, N, X, Y, kd, eta, k, ax, ay);
+        float NdotL = dot(lRec.d, N), NdotV = dot(V, N);  // pdf(:100-115)
+        if (!(NdotL < 0 || NdotV < 0 || ((lRec.flags & EArea) == 0))) {
+          vec3 wi = toLocal(X, Y, N, lRec.d), wo = toLocal(X, Y, N, V);
+          bsdfPdf = importanceAnisoGGXPdf(makeNormal(wi + wo), wo, ax, ay);
+        }
+      }
+      storeDirect(p, visible, w, bsdfPdf, radiance, lRec);
+    }
+    vec2 u = rand2(p.pRec.seed);  // sampleBsdf(:117-149)
+    BsdfSamplingRecord bRec;
+    vec3 weight(0.0f);
+    float NdotV = dot(V, N);
+    if (NdotV <= 0) {
+      bRec.flags = EBsdfNull;
+      bRec.pdf = 0;
+      bRec.d = vec3(0.0f);
+    } else {
+      vec3 wo = toLocal(X, Y, N, V);
+      vec3 wi = importanceSampleAnisoGGX(u, wo, ax, ay);
+      vec3 L = bRec.d = toWorld(X, Y, N, wi);
+      vec3 H = makeNormal(V + L);
+      vec3 wh = makeNormal(wi + wo);
+      float NdotL = dot(N, L);
+      vec3 Fs = conductorReflectance3(eta, k, NdotL);
+      float Gs = g1SmithAnisoGGX(NdotV, dot(V, X), dot(V, Y), ax, ay);
+      Gs *= g1SmithAnisoGGX(NdotL, dot(L, X), dot(L, Y), ax, ay);
+      float Ds = dAnisoGGX(dot(H, N), dot(H, X), dot(H, Y), ax, ay);
+      bRec.flags = EGlossyReflection;
+      bRec.pdf = importanceAnisoGGXPdf(wh, wo, ax, ay);
+      weight = kd * Fs * Gs * Ds * NdotL;
+    }
+    nextRay(p, s, bRec, weight, s.ffN);
+  }
+
+  // ------------------------------------------------------------------ brdf_phong.rchit
+  static vec3 phongEval(vec3 L, vec3 V, vec3 N, vec3 diffuse, vec3 specular, float shininess) {  // :12-31, EArea
+    float NdotL = dot(N, L), NdotV = dot(N, V);
+    if (NdotL < 0 || NdotV < 0) return vec3(0.0f);
+    vec3 H = normalize(L + V);
+    vec3 diffuseLobe = diffuse * INV_PI;
+    vec3 specularLobe = specular * std::pow(std::fmax(dot(H, N), 0.0f), shininess) * (shininess + 2) * INV_2PI;
+    float db = luminance(diffuse), sb = luminance(specular);
+    float diffuseWeight = db / (db + sb), specularWeight = 1 - diffuseWeight;
+    return (diffuseWeight * diffuseLobe + specularWeight * specularLobe) * NdotL;
+  }
+  static float pdfPhong(vec3 L, vec3 V, vec3 N, float shininess) {  // :33-38
+    vec3 H = normalize(L + V);
+    float NdotH = std::fmax(dot(H, N), 0.0f), VdotH = std::fmax(dot(H, V), 0.0f);
+    return (shininess + 1) * INV_2PI * std::pow(NdotH, shininess) * 0.25f / (VdotH + EPS);
+  }
+  void chitPhong(RayPayload& p, HitState& s) const {  // :113-193
+    fetchDiffuse(s);
+    applyNormalMap(s);
+    vec3 diffuse(s.mat.diffuse), specular(s.mat.rhoSpec);
+    float shininess = s.mat.specular;
+    if (p.pRec.depth == 1) {
+      writeChannel(p, pc.diffuseOutChannel, diffuse);
+      writeChannel(p, pc.normalOutChannel, s.ffN);
+      writeChannel(p, pc.specularOutChannel, specular);
+      writeChannel(p, pc.tangentOutChannel, s.X);
+      writeChannel(p, pc.roughnessOutChannel, vec3(1, 1, 0));
+      writeChannel(p, pc.positionOutChannel, s.pos);
+      writeChannel(p, pc.uvOutChannel, vec3(s.uv.x, s.uv.y, 1));
+    }
+    const vec3 N = s.ffN, V = s.V;
+    float db = luminance(diffuse), sb = luminance(specular);
+    float diffuseWeight = db / (db + sb), specularWeight = 1 - diffuseWeight;
+    {
+      bool visible;
+      LightSamplingRecord lRec;
+      vec3 radiance = sampleLights(p, p.pRec.ray.d, s.pos, s.ffN, visible, lRec);
+      vec3 w(0.0f);
+      float bsdfPdf = 0.0f;
+      if (visible) {
+        w = phongEval(lRec.d, V, N, diffuse, specular, shininess);
+        if ((lRec.flags & EArea) != 0)  // pdf(:40-53)
+          bsdfPdf = diffuseWeight * cosineHemispherePdf(dot(N, lRec.d)) + specularWeight * pdfPhong(lRec.d, V, N, shininess);
+      }
+      storeDirect(p, visible, w, bsdfPdf, radiance, lRec);
+    }
+    vec2 u = rand2(p.pRec.seed);  // sampleBsdf(:55-86)
+    BsdfSamplingRecord bRec;
+    if (u.x < diffuseWeight) {
+      u.x /= diffuseWeight;
+      vec3 wi = cosineSampleHemisphere(u);
+      bRec.pdf = cosineHemispherePdf(wi.z);
+      bRec.d = toWorld(s.X, s.Y, N, wi);
+      bRec.flags = EDiffuseReflection;
+    } else {
+      u.x = (u.x - diffuseWeight) / specularWeight;
+      float cosTheta = std::pow(u.x, 1 / (shininess + 1));
+      float phi = TWO_PI * u.y;
+      float sinTheta = safeSqrt(1 - cosTheta * cosTheta);
+      vec3 wh(sinTheta * std::sin(phi), sinTheta * std::cos(phi), cosTheta);
+      vec3 H = toWorld(s.X, s.Y, N, wh);
+      vec3 L = reflect(-V, H);
+      bRec.pdf = pdfPhong(L, V, N, shininess);
+      bRec.d = L;
+      bRec.flags = EGlossyReflection;
+    }
+    vec3 bsdfWeight = phongEval(bRec.d, V, N, diffuse, specular, shininess);
+    if (bRec.pdf <= 0.0f || isBlack(bsdfWeight)) {
+      p.pRec.stop = true;
+      return;
+    }
+    p.bRec = bRec;
+    p.pRec.ray = Ray{offsetPositionAlongNormal(s.pos, s.ffN), bRec.d};
+    p.pRec.throughput *= bsdfWeight / bRec.pdf;
+  }
+
+  // ------------------------------------------------------------------ brdf_disney.rchit
+  struct DisneyMaterial {  // :31-49
+    vec3 baseColor;
+    float anisotropic, metallic, roughness, subsurface, specularTint, sheen, sheenTint, clearcoat, clearcoatRoughness, ior, opacity, ax, ay;
+  };
+  static float GTR1(float NDotH, float a) {  // :55-60
+    if (a >= 1.0f) return INV_PI;
+    float a2 = a * a;
+    float t = 1.0f + (a2 - 1.0f) * NDotH * NDotH;
+    return (a2 - 1.0f) / (PI * std::log(a2) * t);
+  }
+  static vec3 SampleGTR1(float rgh, float r1, float r2) {  // :62-74 (r2 is unused there)
+    float a = std::fmax(0.001f, rgh);
+    float a2 = a * a;
+    float phi = r1 * TWO_PI;
+    float cosTheta = std::sqrt((1.0f - std::pow(a2, 1.0f - r1)) / (1.0f - a2));
+    float sinTheta = clampf(std::sqrt(1.0f - (cosTheta * cosTheta)), 0.0f, 1.0f);
+    return vec3(sinTheta * std::cos(phi), sinTheta * std::sin(phi), cosTheta);
+  }
+  static vec3 SampleGGXVNDF(vec3 V, float ax, float ay, float r1, float r2) {  // :96-114
+    vec3 Vh = normalize(vec3(ax * V.x, ay * V.y, V.z));
+    float lensq = Vh.x * Vh.x + Vh.y * Vh.y;
+    vec3 T1 = lensq > 0 ? vec3(-Vh.y, Vh.x, 0) * (1.0f / std::sqrt(lensq)) : vec3(1, 0, 0);
+    vec3 T2 = cross(Vh, T1);
+    float r = std::sqrt(r1);
+    float phi = 2.0f * PI * r2;
+    float t1 = r * std::cos(phi), t2 = r * std::sin(phi);
+    float sv = 0.5f * (1.0f + Vh.z);
+    t2 = (1.0f - sv) * std::sqrt(1.0f - t1 * t1) + sv * t2;
+    vec3 Nh = t1 * T1 + t2 * T2 + std::sqrt(std::fmax(0.0f, 1.0f - t1 * t1 - t2 * t2)) * Vh;
+    return normalize(vec3(ax * Nh.x, ay * Nh.y, std::fmax(0.0f, Nh.z)));
+  }
+  static float GTR2Aniso(float NDotH, float HDotX, float HDotY, float ax, float ay) {  // :116-121
+    float a = HDotX / ax, b = HDotY / ay;
+    float c = a * a + b * b + NDotH * NDotH;
+    return 1.0f / (PI * ax * ay * c * c);
+  }
+  static float SmithG(float NDotV, float alphaG) {  // :134-138
+    float a = alphaG * alphaG, b = NDotV * NDotV;
+    return (2.0f * NDotV) / (NDotV + std::sqrt(a + b - a * b));
+  }
+  static float SmithGAniso(float NDotV, float VDotX, float VDotY, float ax, float ay) {  // :140-145
+    float a = VDotX * ax, b = VDotY * ay, c = NDotV;
+    return (2.0f * NDotV) / (NDotV + std::sqrt(a * a + b * b + c * c));
+  }
+  static float SchlickFresnel(float u) {  // :147-151
+    float m = clampf(1.0f - u, 0.0f, 1.0f);
+    float m2 = m * m;
+    return m2 * m2 * m;
+  }
+  static float DisneyFresnel(float metallic, float eta, float LDotH, float VDotH) {  // :167-171 (DielectricFresnel :153-165 == dielectric's)
+    return mixf(dielectricFresnel(std::fabs(VDotH), eta), SchlickFresnel(LDotH), metallic);
+  }
+  static vec3 EvalDiffuse(const DisneyMaterial& mat, vec3 Csheen, vec3 V, vec3 L, vec3 H, float& pdf) {  // :173-197
+    pdf = 0.0f;
+    if (L.z <= 0.0f) return vec3(0.0f);
+    float FL = SchlickFresnel(L.z), FV = SchlickFresnel(V.z), FH = SchlickFresnel(dot(L, H));
+    float Fd90 = 0.5f + 2.0f * dot(L, H) * dot(L, H) * mat.roughness;
+    float Fd = mixf(1.0f, Fd90, FL) * mixf(1.0f, Fd90, FV);
+    float Fss90 = dot(L, H) * dot(L, H) * mat.roughness;
+    float Fss = mixf(1.0f, Fss90, FL) * mixf(1.0f, Fss90, FV);
+    float ss = 1.25f * (Fss * (1.0f / (L.z + V.z) - 0.5f) + 0.5f);
+    vec3 Fsheen = FH * mat.sheen * Csheen;
+    pdf = L.z * INV_PI;
+    return (1.0f - mat.metallic) * (INV_PI * mixf(Fd, ss, mat.subsurface) * mat.baseColor + Fsheen);
+  }
+  static vec3 EvalSpecReflection(const DisneyMaterial& mat, float eta, vec3 specCol, vec3 V, vec3 L, vec3 H, float& pdf) {  // :199-212
+    pdf = 0.0f;
+    if (L.z <= 0.0f) return vec3(0.0f);
+    float FM = DisneyFresnel(mat.metallic, eta, dot(L, H), dot(V, H));
+    vec3 F = mix3(specCol, vec3(1.0f), FM);
+    float D = GTR2Aniso(H.z, H.x, H.y, mat.ax, mat.ay);
+    float G1 = SmithGAniso(std::fabs(V.z), V.x, V.y, mat.ax, mat.ay);
+    float G2 = G1 * SmithGAniso(std::fabs(L.z), L.x, L.y, mat.ax, mat.ay);
+    pdf = G1 * D / (4.0f * V.z);
+    return F * D * G2 / (4.0f * L.z * V.z);
+  }
+  static vec3 EvalClearcoat(const DisneyMaterial& mat, vec3 V, vec3 L, vec3 H, float& pdf) {  // :214-226
+    pdf = 0.0f;
+    if (L.z <= 0.0f) return vec3(0.0f);
+    float FH = dielectricFresnel(dot(V, H), 1.0f / 1.5f);
+    float F = mixf(0.04f, 1.0f, FH);
+    float D = GTR1(H.z, mat.clearcoatRoughness);
+    float G = SmithG(L.z, 0.25f) * SmithG(V.z, 0.25f);
+    float jacobian = 1.0f / (4.0f * dot(V, H));
+    pdf = D * H.z * jacobian;
+    return vec3(0.25f) * mat.clearcoat * F * D * G / (4.0f * L.z * V.z);
+  }
+  static void GetSpecColor(const DisneyMaterial& mat, float eta, vec3& specCol, vec3& sheenCol) {  // :228-236
+    float lum = Luminance709(mat.baseColor);
+    vec3 ctint = lum > 0.0f ? mat.baseColor / lum : vec3(1.0f);
+    float F0 = (1.0f - eta) / (1.0f + eta);
+    specCol = mix3(F0 * F0 * mix3(vec3(1.0f), ctint, mat.specularTint), mat.baseColor, mat.metallic);
+    sheenCol = mix3(vec3(1.0f), ctint, mat.sheenTint);
+  }
+  static void GetLobeProbabilities(const DisneyMaterial& mat, vec3 specCol, float approxFresnel, float& diffuseWt, float& specReflectWt,
+                                   float& clearcoatWt) {  // :238-250
+    diffuseWt = Luminance709(mat.baseColor) * (1.0f - mat.metallic);
+    specReflectWt = Luminance709(mix3(specCol, vec3(1.0f), approxFresnel));
+    clearcoatWt = 0.25f * mat.clearcoat * (1.0f - mat.metallic);
+    float totalWt = diffuseWt + specReflectWt + clearcoatWt;
+    diffuseWt /= totalWt, specReflectWt /= totalWt, clearcoatWt /= totalWt;
+  }
+  static vec3 disneyEval(vec3 L, vec3 V, vec3 N, vec3 X, vec3 Y, const DisneyMaterial& mat, float eta, float& bsdfPdf) {  // :252-300, EArea
+    vec3 weight(0.0f);
+    bsdfPdf = 0.0f;
+    V = toLocal(X, Y, N, V);
+    L = toLocal(X, Y, N, L);
+    if (L.z <= 0 || V.z <= 0) return weight;
+    vec3 H = normalize(L + V);
+    if (H.z < 0.0f) H = -H;
+    vec3 specCol, sheenCol;
+    GetSpecColor(mat, eta, specCol, sheenCol);
+    float diffuseWt, specReflectWt, clearcoatWt;
+    float fresnel = DisneyFresnel(mat.metallic, eta, dot(L, H), dot(V, H));
+    GetLobeProbabilities(mat, specCol, fresnel, diffuseWt, specReflectWt, clearcoatWt);
+    float pdf = 0.0f;
+    if (diffuseWt > 0.0f && L.z > 0.0f) {
+      weight += EvalDiffuse(mat, sheenCol, V, L, H, pdf);
+      bsdfPdf += pdf * diffuseWt;
+    }
+    if (specReflectWt > 0.0f && L.z > 0.0f && V.z > 0.0f) {
+      weight += EvalSpecReflection(mat, eta, specCol, V, L, H, pdf);
+      bsdfPdf += pdf * specReflectWt;
+    }
+    if (clearcoatWt > 0.0f && L.z > 0.0f && V.z > 0.0f) {
+      weight += EvalClearcoat(mat, V, L, H, pdf);
+      bsdfPdf += pdf * clearcoatWt;
+    }
+    return weight * L.z;
+  }
+  void chitDisney(RayPayload& p, HitState& s) const {  // :373-487
+    fetchDiffuse(s);
+    if (s.mat.metalnessTextureId >= 0) s.mat.metalness = textureEval(s.mat.metalnessTextureId, s.uv).x;
+    if (s.mat.roughnessTextureId >= 0) s.mat.roughness = textureEval(s.mat.roughnessTextureId, s.uv).x;
+    applyNormalMap(s);
+    float opacity = s.mat.rhoSpec[0];
+    if (s.mat.opacityTextureId >= 0) opacity = textureEval(s.mat.opacityTextureId, s.uv).x;
+    if (passThrough(p, s, opacity)) return;
+    DisneyMaterial mat;
+    {
+      float aspect = std::sqrt(1.0f - s.mat.anisotropic * 0.9f);
+      mat.ax = std::fmax(0.001f, s.mat.roughness * s.mat.roughness / aspect);
+      mat.ay = std::fmax(0.001f, s.mat.roughness * s.mat.roughness * aspect);
+      mat.baseColor = vec3(s.mat.diffuse);
+      mat.anisotropic = s.mat.anisotropic;
+      mat.metallic = s.mat.metalness;
+      mat.roughness = std::fmax(s.mat.roughness * s.mat.roughness, 0.001f);
+      mat.subsurface = s.mat.subsurface;
+      mat.specularTint = s.mat.specularTint;
+      mat.sheen = s.mat.sheen;
+      mat.sheenTint = s.mat.sheenTint;
+      mat.clearcoat = s.mat.clearcoat;
+      mat.clearcoatRoughness = mixf(0.1f, 0.001f, s.mat.clearcoatGloss);
+      mat.ior = s.mat.ior;
+      mat.opacity = opacity;
+    }
+    float eta = dot(s.V, s.N) > 0.0f ? (1.0f / mat.ior) : mat.ior;
+    const vec3 N = s.ffN, X = s.X, Y = s.Y;
+    {
+      bool visible;
+      LightSamplingRecord lRec;
+      vec3 radiance = sampleLights(p, p.pRec.ray.d, s.pos, s.ffN, visible, lRec);
+      vec3 w(0.0f);
+      float bsdfPdf = 0.0f;
+      if (visible) w = disneyEval(lRec.d, s.V, N, X, Y, mat, eta, bsdfPdf);  // always called with EArea (:449-450)
+      storeDirect(p, visible, w, bsdfPdf, radiance, lRec);
+    }
+    vec2 u = rand2(p.pRec.seed);  // sampleBsdf(:302-371)
+    BsdfSamplingRecord bRec;
+    float pdf = 0.0f;
+    vec3 f(0.0f);
+    float r1 = u.x, r2 = u.y;
+    vec3 V = toLocal(X, Y, N, s.V), L;
+    vec3 specCol, sheenCol;
+    GetSpecColor(mat, eta, specCol, sheenCol);
+    float diffuseWt, specReflectWt, clearcoatWt;
+    float approxFresnel = DisneyFresnel(mat.metallic, eta, V.z, V.z);
+    GetLobeProbabilities(mat, specCol, approxFresnel, diffuseWt, specReflectWt, clearcoatWt);
+    float cdf0 = diffuseWt, cdf1 = cdf0 + clearcoatWt;
+    if (r1 < cdf0) {
+      r1 /= cdf0;
+      L = cosineSampleHemisphere(vec2{r1, r2});
+      vec3 H = normalize(L + V);
+      f = EvalDiffuse(mat, sheenCol, V, L, H, pdf);
+      pdf *= diffuseWt;
+      bRec.flags = EDiffuseReflection;
+    } else if (r1 < cdf1) {
+      r1 = (r1 - cdf0) / (cdf1 - cdf0);
+      vec3 H = SampleGTR1(mat.clearcoatRoughness, r1, r2);
+      if (H.z < 0.0f) H = -H;
+      L = normalize(reflect(-V, H));
+      f = EvalClearcoat(mat, V, L, H, pdf);
+      pdf *= clearcoatWt;
+      bRec.flags = EGlossyReflection;
+    } else {
+      r1 = (r1 - cdf1) / (1.0f - cdf1);
+      vec3 H = SampleGGXVNDF(V, mat.ax, mat.ay, r1, r2);
+      if (H.z < 0.0f) H = -H;
+      L = normalize(reflect(-V, H));
+      f = EvalSpecReflection(mat, eta, specCol, V, L, H, pdf);
+      pdf *= specReflectWt;
+      bRec.flags = EGlossyReflection;
+    }
+    bRec.d = toWorld(X, Y, N, L);
+    bRec.pdf = pdf;
+    // `abs(dot(N, L))` at :370 mixes the world-space normal with the local-space direction, as written
+    vec3 bsdfWeight = f * std::fabs(dot(N, L));
+    if (bRec.pdf <= 0.0f || isBlack(bsdfWeight)) {
+      p.pRec.stop = true;
+      return;
+    }
+    p.bRec = bRec;
+    p.pRec.ray = Ray{offsetPositionAlongNormal(s.pos, s.ffN), bRec.d};
+    p.pRec.throughput *= bsdfWeight / bRec.pdf;
+  }
+
   // ------------------------------------------------------------------ brdf_plastic.rchit
   void chitPlastic(RayPayload& p, HitState& s) const {  // :133-204
     fetchDiffuse(s);
@@ -1050,6 +1435,10 @@ struct oracle_ctx {
       case ASUNA_MAT_ROUGH_PLASTIC: chitRoughPlastic(p, s); break;
       case ASUNA_MAT_PBR_METALNESS_ROUGHNESS: chitPbr(p, s); break;
       case ASUNA_MAT_KANG18: chitKang18(p, s, in); break;
+      case ASUNA_MAT_MIRROR: chitMirror(p, s); break;
+      case ASUNA_MAT_ROUGH_CONDUCTOR: chitRoughConductor(p, s); break;
+      case ASUNA_MAT_PHONG: chitPhong(p, s); break;
+      case ASUNA_MAT_DISNEY: chitDisney(p, s); break;
       default: p.pRec.stop = true; return -1;
     }
     return 0;

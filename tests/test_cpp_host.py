@@ -42,6 +42,7 @@ def read_dump(path):
 SCENES = {
     "cornell": lambda: scenes.cornell(32, 24, spp=3, depth=4),
     "materials": lambda: scenes.cornell_materials(24, 16, spp=2, depth=4, env=True, lights="all", textured=True),
+    "all_materials": lambda: scenes.cornell_all_materials(24, 16, spp=2, depth=4, env=True, lights="all", textured=True),
     "pbr": lambda: scenes.pbr_spheres(24, 16, spp=2, depth=3, subdiv=2, tex_size=8),
     "field": lambda: scenes.instanced_field(16, 16, spp=1, depth=2, subdiv=1, grid=2),
 }

@@ -61,6 +61,8 @@ SCENES = {
     "materials_env_only": lambda: scenes.cornell_materials(64, 48, spp=8, env=True, lights="none", textured=False),
     "materials_point": lambda: scenes.cornell_materials(64, 48, spp=8, env=False, lights="point", textured=False),
     "materials_distant_mesh": lambda: scenes.cornell_materials(64, 48, spp=8, env=False, lights="mesh", textured=True),
+    "all_twelve_materials": lambda: scenes.cornell_all_materials(96, 72, spp=8, env=False, lights="all", textured=True),
+    "all_twelve_materials_env": lambda: scenes.cornell_all_materials(96, 72, spp=8, env=True, lights="rect", textured=False),
     "glass_blob": lambda: scenes.glass_blob(128, 72, spp=8, depth=8, subdiv=4, env_size=(128, 64)),
     "pbr_sunsky": lambda: scenes.pbr_spheres(128, 72, spp=8, depth=5, subdiv=4, tex_size=64),
     "instanced_field": lambda: scenes.instanced_field(128, 72, spp=8, depth=5, subdiv=3, grid=4),
@@ -102,6 +104,7 @@ def test_use_face_normal_and_ignore_emissive(gpu_ctx, cpu_ctx):
     ("materials_48x36_spp4", lambda: scenes.cornell_materials(48, 36, spp=4, depth=5, env=False, lights="all", textured=True)),
     ("materials_env_48x36_spp4", lambda: scenes.cornell_materials(48, 36, spp=4, depth=5, env=True, lights="rect", textured=True)),
     ("pbr_sunsky_48x27_spp4", lambda: scenes.pbr_spheres(48, 27, spp=4, depth=4, subdiv=3, tex_size=32)),
+    ("all_materials_48x36_spp4", lambda: scenes.cornell_all_materials(48, 36, spp=4, depth=5, env=True, lights="all", textured=True)),
 ])
 def test_against_committed_golden_fixtures(gpu_ctx, name, builder):
     """Fixtures frozen from the oracle by tools/make_golden.py; this test needs no oracle at run time."""
@@ -139,9 +142,9 @@ def test_error_behaviour(gpu_ctx):
     with pytest.raises(capi.AsunaError):
         gpu_ctx.render_frames(1)  # nothing uploaded
     m = S.default_material()
-    m["type"] = S.MAT_DISNEY
+    m["type"] = 12
     with pytest.raises(capi.AsunaError):
-        gpu_ctx.add_material(m)  # outside the hot-path scope
+        gpu_ctx.add_material(m)  # not one of the twelve material types (src/shared/material.h:7-21)
     v = host.make_vertices([[0, 0, 0], [1, 0, 0], [0, 1, 0]])
     with pytest.raises(capi.AsunaError):
         gpu_ctx.add_mesh(v, [0, 1, 3])  # index out of range

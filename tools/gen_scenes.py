@@ -56,7 +56,19 @@ def _material_json(sc, name, m):
         if t == S.MAT_ROUGH_PLASTIC:
             js["alpha"] = [float(x) for x in m["anisoAlpha"]]
             tex("roughnessTextureId", "alpha_texture")
-    elif t == S.MAT_CONDUCTOR:
+    elif t == S.MAT_DISNEY:
+        js.update(diffuse_reflectance=v3("diffuse"), metallic=float(m["metalness"]), roughness=float(m["roughness"]),
+                  opacity=float(m["rhoSpec"][0]))
+        tex("diffuseTextureId", "diffuse_texture"), tex("normalTextureId", "normal_texture")
+        tex("metalnessTextureId", "metallic_texture"), tex("roughnessTextureId", "roughness_texture")
+        tex("opacityTextureId", "opacity_texture")
+    elif t == S.MAT_PHONG:
+        js.update(diffuse_reflectance=v3("diffuse"), specular_reflectance=v3("rhoSpec"), shininess=float(m["specular"]))
+        tex("diffuseTextureId", "diffuse_texture"), tex("normalTextureId", "normal_texture")
+    elif t in (S.MAT_CONDUCTOR, S.MAT_ROUGH_CONDUCTOR):
+        if t == S.MAT_ROUGH_CONDUCTOR:
+            js["alpha"] = [float(x) for x in m["anisoAlpha"]]
+            tex("roughnessTextureId", "alpha_texture")
         for metal, (eta, k) in host.COMPLEX_IOR.items():
             if np.allclose(eta, m["radiance"], atol=1e-6) and np.allclose(k, m["radianceFactor"], atol=1e-6):
                 js["material"] = metal

@@ -73,3 +73,4 @@ render(scenes.cornell(48, 48, spp=4, depth=5), "cornell_48_spp4")
 render(scenes.cornell_materials(48, 36, spp=4, depth=5, env=False, lights="all", textured=True), "materials_48x36_spp4")
 render(scenes.cornell_materials(48, 36, spp=4, depth=5, env=True, lights="rect", textured=True), "materials_env_48x36_spp4")
 render(scenes.pbr_spheres(48, 27, spp=4, depth=4, subdiv=3, tex_size=32), "pbr_sunsky_48x27_spp4")
+render(scenes.cornell_all_materials(48, 36, spp=4, depth=5, env=True, lights="all", textured=True), "all_materials_48x36_spp4")
