@@ -58,7 +58,7 @@ struct asuna_ctx {
   WideNode *d_blas_nodes = nullptr, *d_tlas_nodes = nullptr;
   BuildResult* d_build_results = nullptr;
   TriSlot* d_tris = nullptr;
-  uint32_t* d_tlas_leaf_inst = nullptr;
+  uint32_t *d_tlas_leaf_inst = nullptr, *d_tlas_ids = nullptr;
   DInstance* d_instances = nullptr;
   DMesh* d_meshes = nullptr;
   AsunaMaterial* d_materials = nullptr;
@@ -165,6 +165,7 @@ void free_scene_device(asuna_ctx* ctx) {
   free_dev(ctx->d_tlas_nodes);
   free_dev(ctx->d_tris);
   free_dev(ctx->d_tlas_leaf_inst);
+  free_dev(ctx->d_tlas_ids);
   free_dev(ctx->d_instances);
   free_dev(ctx->d_meshes);
   free_dev(ctx->d_materials);
@@ -447,48 +448,93 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   free_scene_device(ctx);
   cudaStream_t s = ctx->stream;
 
+  // Flattening: meshes used by exactly one instance are taken to world space at build time and share ONE merged
+  // BLAS ("world BLAS"), so a ray pays neither a transform nor a second tree for them; instanced meshes keep
+  // their own object-space BLAS.  When every instance is merged the top level disappears (single-level
+  // traversal).  ASUNA_FLATTEN=0 keeps the plain two-level structure (A/B experiments, tests).
+  uint32_t n_inst = (uint32_t)ctx->instances.size(), n_mesh = (uint32_t)ctx->meshes.size();
+  std::vector<uint32_t> uses(n_mesh, 0);
+  for (auto& in : ctx->instances) uses[in.mesh]++;
+  bool flatten = true;
+  if (const char* f = getenv("ASUNA_FLATTEN")) flatten = atoi(f) != 0;
+  std::vector<uint32_t> merged, tlas_ids;  // instance ids in the world BLAS / instance records under the top level
+  for (uint32_t i = 0; i < n_inst; i++)
+    (flatten && uses[ctx->instances[i].mesh] == 1 ? merged : tlas_ids).push_back(i);
+  if (merged.size() == 1 && !tlas_ids.empty()) tlas_ids.push_back(merged[0]), merged.clear();  // nothing to merge with
+  std::vector<char> mesh_merged(n_mesh, 0);
+  for (uint32_t i : merged) mesh_merged[ctx->instances[i].mesh] = 1;
+  std::sort(tlas_ids.begin(), tlas_ids.end());
+  const bool have_world = !merged.empty();
+  const bool single_level = have_world && tlas_ids.empty();
+  if (have_world) tlas_ids.push_back(n_inst);  // the world BLAS enters the top level as pseudo-instance n_inst
+  const uint32_t n_tlas = (uint32_t)tlas_ids.size();
+
   // layout of the node / triangle pools
   size_t total_nodes = 0, total_tris = 0;
-  uint32_t max_prims = (uint32_t)ctx->instances.size();
-  for (auto& m : ctx->meshes) {
+  uint32_t max_prims = n_tlas, world_tris = 0;
+  for (uint32_t i = 0; i < n_mesh; i++) {
+    HostMesh& m = ctx->meshes[i];
+    if (mesh_merged[i]) {
+      m.node_base = m.tri_base = -1;
+      world_tris += m.n_tris;
+      continue;
+    }
     m.node_base = (int)total_nodes;
     m.tri_base = (int)total_tris;
     total_nodes += std::max<uint32_t>(m.n_tris - 1, 1);
     total_tris += m.n_tris;
     max_prims = std::max(max_prims, m.n_tris);
   }
+  const size_t world_node_base = total_nodes, world_tri_base = total_tris;
+  if (have_world) {
+    total_nodes += std::max<uint32_t>(world_tris - 1, 1);
+    total_tris += world_tris;
+    max_prims = std::max(max_prims, world_tris);
+  }
   if (total_tris >= (1u << 27)) return fail(ctx, ASUNA_E_INVALID, "more than 2^27 triangles");
-  uint32_t n_inst = (uint32_t)ctx->instances.size(), n_mesh = (uint32_t)ctx->meshes.size();
   ASUNA_CUDA_CHECK(ctx->scratch.reserve(max_prims));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_blas_nodes, total_nodes * sizeof(WideNode)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_build_results, (n_mesh + 1) * sizeof(BuildResult)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_build_results, (n_mesh + 2) * sizeof(BuildResult)));
+  ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->d_build_results, 0, (n_mesh + 2) * sizeof(BuildResult), s));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tris, total_tris * sizeof(TriSlot)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_nodes, std::max<uint32_t>(n_inst - 1, 1) * sizeof(WideNode)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_leaf_inst, n_inst * sizeof(uint32_t)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_instances, n_inst * sizeof(DInstance)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_nodes, std::max<uint32_t>(n_tlas - 1, 1) * sizeof(WideNode)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_leaf_inst, n_tlas * sizeof(uint32_t)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_ids, n_tlas * sizeof(uint32_t)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_instances, (n_inst + 1) * sizeof(DInstance)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_meshes, n_mesh * sizeof(DMesh)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_mesh_lo, n_mesh * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_mesh_hi, n_mesh * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_mesh_lo, (n_mesh + 1) * sizeof(float4)));
+  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_mesh_hi, (n_mesh + 1) * sizeof(float4)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_materials, std::max<size_t>(ctx->materials.size(), 1) * sizeof(AsunaMaterial)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_lights, std::max<size_t>(ctx->lights.size(), 1) * sizeof(AsunaLight)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_textures, std::max<size_t>(ctx->textures.size(), 1) * sizeof(DTexture)));
+  TriSlot* d_soup = nullptr;  // world-space triangles in input order; the emit kernel copies them into leaf order
+  if (have_world) ASUNA_CUDA_CHECK(cudaMalloc(&d_soup, (size_t)world_tris * sizeof(TriSlot)));
 
   // flat tables
-  std::vector<DInstance> hinst(n_inst);
+  std::vector<DInstance> hinst(n_inst + 1);
   for (uint32_t i = 0; i < n_inst; i++) {
     const HostInstance& in = ctx->instances[i];
     DInstance d{};
     make_instance_matrices(in.xform, d);
-    d.blas_root = ctx->meshes[in.mesh].node_base;
+    d.blas_root = ctx->meshes[in.mesh].node_base;  // -1: lives in the world BLAS
     d.mesh = in.mesh, d.material = in.material, d.light = in.light;
     d.mat_type = in.light >= 0 ? 0xFFFFFFFFu : ctx->materials[in.material].type;
     hinst[i] = d;
+  }
+  {  // pseudo-instance of the world BLAS: identity transform, "mesh" n_mesh (its box slot)
+    static const float ident[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    DInstance d{};
+    make_instance_matrices(ident, d);
+    d.blas_root = (int32_t)world_node_base;
+    d.mesh = n_mesh, d.material = 0, d.light = -1, d.mat_type = 0;
+    hinst[n_inst] = d;
   }
   std::vector<DMesh> hmesh(n_mesh);
   for (uint32_t i = 0; i < n_mesh; i++) hmesh[i] = DMesh{ctx->meshes[i].d_vertices, ctx->meshes[i].d_indices, ctx->meshes[i].n_tris, 0};
   std::vector<DTexture> htex(ctx->textures.size());
   for (size_t i = 0; i < htex.size(); i++) htex[i] = DTexture{ctx->textures[i].d_texels, (int)ctx->textures[i].w, (int)ctx->textures[i].h};
-  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_instances, hinst.data(), n_inst * sizeof(DInstance), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_instances, hinst.data(), (n_inst + 1) * sizeof(DInstance), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_tlas_ids, tlas_ids.data(), n_tlas * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_meshes, hmesh.data(), n_mesh * sizeof(DMesh), cudaMemcpyHostToDevice, s));
   if (!ctx->materials.empty())
     ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_materials, ctx->materials.data(), ctx->materials.size() * sizeof(AsunaMaterial), cudaMemcpyHostToDevice, s));
@@ -510,20 +556,34 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   }
   for (uint32_t i = 0; i < n_mesh; i++) {
     HostMesh& m = ctx->meshes[i];
+    if (mesh_merged[i]) continue;
     launch_tri_boxes(s, m.d_vertices, m.d_indices, m.n_tris, ctx->scratch);
     PrimPayload pl;
     pl.vertices = m.d_vertices, pl.indices = m.d_indices, pl.tris = ctx->d_tris;
     ASUNA_CUDA_CHECK(launch_build_wide(s, m.n_tris, ctx->d_blas_nodes, (uint32_t)m.node_base, (uint32_t)m.tri_base, ctx->scratch,
                                        pl, cost_prim, ctx->d_mesh_lo + i, ctx->d_mesh_hi + i, ctx->d_build_results + i));
   }
+  if (have_world) {  // the world BLAS over the single-use instances
+    uint32_t off = 0;
+    for (uint32_t i : merged) {
+      const HostMesh& m = ctx->meshes[ctx->instances[i].mesh];
+      launch_world_triangles(s, m.d_vertices, m.d_indices, m.n_tris, hinst[i].o2w, i, d_soup, off, off == 0, ctx->scratch);
+      off += m.n_tris;
+    }
+    PrimPayload pl;
+    pl.soup = d_soup, pl.tris = ctx->d_tris;
+    ASUNA_CUDA_CHECK(launch_build_wide(s, world_tris, ctx->d_blas_nodes, (uint32_t)world_node_base, (uint32_t)world_tri_base,
+                                       ctx->scratch, pl, cost_prim, ctx->d_mesh_lo + n_mesh, ctx->d_mesh_hi + n_mesh,
+                                       ctx->d_build_results + n_mesh));
+  }
   // top level over the instance boxes (≙ createTopLevelAS); entering an instance costs a ray transform
   // plus a whole mesh BVH, so leaves are kept to single instances wherever the SAH allows
-  launch_instance_boxes(s, ctx->d_instances, ctx->d_mesh_lo, ctx->d_mesh_hi, n_inst, ctx->scratch);
+  launch_instance_boxes(s, ctx->d_instances, ctx->d_tlas_ids, ctx->d_mesh_lo, ctx->d_mesh_hi, n_tlas, ctx->scratch);
   {
     PrimPayload pl;
-    pl.leaf_inst = ctx->d_tlas_leaf_inst;
-    ASUNA_CUDA_CHECK(launch_build_wide(s, n_inst, ctx->d_tlas_nodes, 0, 0, ctx->scratch, pl, 4.0f, nullptr, nullptr,
-                                       ctx->d_build_results + n_mesh));
+    pl.leaf_inst = ctx->d_tlas_leaf_inst, pl.prim_ids = ctx->d_tlas_ids;
+    ASUNA_CUDA_CHECK(launch_build_wide(s, n_tlas, ctx->d_tlas_nodes, 0, 0, ctx->scratch, pl, 4.0f, nullptr, nullptr,
+                                       ctx->d_build_results + n_mesh + 1));
   }
   cudaEventRecord(e1, s);
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
@@ -537,14 +597,14 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
 
   // statistics for asuna_accel_stats: wide nodes in use, primitive slots, SAH cost summed over the BLASes
   {
-    std::vector<BuildResult> res(n_mesh + 1);
+    std::vector<BuildResult> res(n_mesh + 2);
     ASUNA_CUDA_CHECK(cudaMemcpy(res.data(), ctx->d_build_results, res.size() * sizeof(BuildResult), cudaMemcpyDeviceToHost));
     uint64_t nodes = 0, prims = 0;
     double cost = 0.0;
-    for (uint32_t i = 0; i < n_mesh; i++) nodes += res[i].wide_nodes, prims += res[i].prim_slots, cost += res[i].sah_cost;
+    for (uint32_t i = 0; i <= n_mesh; i++) nodes += res[i].wide_nodes, prims += res[i].prim_slots, cost += res[i].sah_cost;
     ctx->accel_stats[0] = nodes;
     ctx->accel_stats[1] = prims;
-    ctx->accel_stats[2] = res[n_mesh].wide_nodes;
+    ctx->accel_stats[2] = res[n_mesh + 1].wide_nodes;
     ctx->accel_stats[3] = (uint64_t)(cost * 1000.0);
   }
 
@@ -559,6 +619,9 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   ctx->view.textures = ctx->d_textures;
   for (int k = 0; k < 3; k++) ctx->view.env[k] = DTexture{ctx->env[k].d_texels, (int)ctx->env[k].w, (int)ctx->env[k].h};
   ctx->view.n_instances = n_inst;
+  ctx->view.world_inst = have_world ? n_inst : 0xFFFFFFFFu;
+  ctx->view.single_root = single_level ? (uint32_t)world_node_base : 0xFFFFFFFFu;
+  free_dev(d_soup);
   ctx->view.magic = 0x4B000000u;
   ctx->view.refill_lanes = 8, ctx->view.tri_vote_shift = 2;
   if (const char* t = getenv("ASUNA_TUNE")) {  // "refill,shift[,cost_prim x10]" -- traversal tuning experiments

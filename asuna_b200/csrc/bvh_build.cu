@@ -85,15 +85,45 @@ __global__ void k_tri_boxes(const AsunaVertex* __restrict__ v, const uint32_t* _
   reduce_bounds(lo, hi, valid, bounds);
 }
 
-// World box of an instance = box of the 8 transformed corners of its mesh box (what a TLAS build sees).
-__global__ void k_instance_boxes(const DInstance* __restrict__ inst, const float4* __restrict__ mesh_lo,
-                                 const float4* __restrict__ mesh_hi, uint32_t n, float4* __restrict__ blo,
-                                 float4* __restrict__ bhi, int* bounds) {
+// Triangles of a single-use instance taken to world space once, at build time: the merged world-space BLAS
+// (api.cu, "flattening") is built over this soup, so rays never pay a transform or a second tree for them.
+// v' = o2w * v with a fixed fma order; the slot keeps (primitive id, instance id) in the two free w lanes.
+__device__ __forceinline__ float4 world_vertex(const float* p, float4 r0, float4 r1, float4 r2, float w) {
+  return make_float4(__fmaf_rn(r0.z, p[2], __fmaf_rn(r0.y, p[1], __fmaf_rn(r0.x, p[0], r0.w))),
+                     __fmaf_rn(r1.z, p[2], __fmaf_rn(r1.y, p[1], __fmaf_rn(r1.x, p[0], r1.w))),
+                     __fmaf_rn(r2.z, p[2], __fmaf_rn(r2.y, p[1], __fmaf_rn(r2.x, p[0], r2.w))), w);
+}
+__global__ void k_world_triangles(const AsunaVertex* __restrict__ v, const uint32_t* __restrict__ idx, uint32_t n,
+                                  float4 r0, float4 r1, float4 r2, uint32_t inst, TriSlot* __restrict__ soup,
+                                  float4* __restrict__ blo, float4* __restrict__ bhi, int* bounds) {
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = i < n;
   float3 lo = make_float3(0, 0, 0), hi = lo;
   if (valid) {
-    const DInstance& in = inst[i];
+    TriSlot t;
+    t.v0 = world_vertex(v[idx[3 * (size_t)i + 0]].pos, r0, r1, r2, __uint_as_float(i));
+    t.v1 = world_vertex(v[idx[3 * (size_t)i + 1]].pos, r0, r1, r2, __uint_as_float(inst));
+    t.v2 = world_vertex(v[idx[3 * (size_t)i + 2]].pos, r0, r1, r2, 0.f);
+    soup[i] = t;
+    lo = make_float3(fminf(t.v0.x, fminf(t.v1.x, t.v2.x)), fminf(t.v0.y, fminf(t.v1.y, t.v2.y)),
+                     fminf(t.v0.z, fminf(t.v1.z, t.v2.z)));
+    hi = make_float3(fmaxf(t.v0.x, fmaxf(t.v1.x, t.v2.x)), fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)),
+                     fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
+    blo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
+    bhi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
+  }
+  reduce_bounds(lo, hi, valid, bounds);
+}
+
+// World box of an instance = box of the 8 transformed corners of its mesh box (what a TLAS build sees).
+__global__ void k_instance_boxes(const DInstance* __restrict__ inst, const uint32_t* __restrict__ ids,
+                                 const float4* __restrict__ mesh_lo, const float4* __restrict__ mesh_hi, uint32_t n,
+                                 float4* __restrict__ blo, float4* __restrict__ bhi, int* bounds) {
+  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  bool valid = i < n;
+  float3 lo = make_float3(0, 0, 0), hi = lo;
+  if (valid) {
+    const DInstance& in = inst[ids ? ids[i] : i];
     float4 ml = mesh_lo[in.mesh], mh = mesh_hi[in.mesh];
     lo = make_float3(FLT_MAX, FLT_MAX, FLT_MAX);
     hi = make_float3(-FLT_MAX, -FLT_MAX, -FLT_MAX);
@@ -445,6 +475,8 @@ struct EmitParams {
   // primitive payload: triangles of a mesh, or instance ids of the top level
   const AsunaVertex* v;
   const uint32_t* idx;
+  const TriSlot* soup;      // world-space triangles of the merged BLAS (then v / idx are unused)
+  const uint32_t* prim_ids; // top level: primitive -> instance index (nullptr = identity)
   TriSlot* tris;
   uint32_t* leaf_inst;
   // results for the host / the top-level build
@@ -458,7 +490,9 @@ __device__ __forceinline__ uint32_t pack4(const uint8_t* b) {
 }
 
 __device__ void emit_prim(const EmitParams& a, uint32_t slot, uint32_t prim) {
-  if (a.tris) {
+  if (a.soup) {
+    a.tris[slot] = a.soup[prim];
+  } else if (a.tris) {
     const float* p0 = a.v[a.idx[3 * (size_t)prim + 0]].pos;
     const float* p1 = a.v[a.idx[3 * (size_t)prim + 1]].pos;
     const float* p2 = a.v[a.idx[3 * (size_t)prim + 2]].pos;
@@ -468,7 +502,7 @@ __device__ void emit_prim(const EmitParams& a, uint32_t slot, uint32_t prim) {
     t.v2 = make_float4(p2[0], p2[1], p2[2], 0.f);
     a.tris[slot] = t;
   } else {
-    a.leaf_inst[slot] = prim;
+    a.leaf_inst[slot] = a.prim_ids ? a.prim_ids[prim] : prim;
   }
 }
 
@@ -724,10 +758,17 @@ void launch_tri_boxes(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx,
   k_tri_boxes<<<div_up(n, kThreads), kThreads, 0, s>>>(v, idx, n, sc.blo, sc.bhi, sc.bounds);
 }
 
-void launch_instance_boxes(cudaStream_t s, const DInstance* inst, const float4* mesh_lo, const float4* mesh_hi,
-                           uint32_t n, BuildScratch& sc) {
+void launch_world_triangles(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, const float4 o2w[3],
+                            uint32_t inst, TriSlot* soup, uint32_t offset, bool first, BuildScratch& sc) {
+  if (first) k_bounds_init<<<1, 32, 0, s>>>(sc.bounds);
+  k_world_triangles<<<div_up(n, kThreads), kThreads, 0, s>>>(v, idx, n, o2w[0], o2w[1], o2w[2], inst, soup + offset,
+                                                             sc.blo + offset, sc.bhi + offset, sc.bounds);
+}
+
+void launch_instance_boxes(cudaStream_t s, const DInstance* inst, const uint32_t* ids, const float4* mesh_lo,
+                           const float4* mesh_hi, uint32_t n, BuildScratch& sc) {
   k_bounds_init<<<1, 32, 0, s>>>(sc.bounds);
-  k_instance_boxes<<<div_up(n, kThreads), kThreads, 0, s>>>(inst, mesh_lo, mesh_hi, n, sc.blo, sc.bhi, sc.bounds);
+  k_instance_boxes<<<div_up(n, kThreads), kThreads, 0, s>>>(inst, ids, mesh_lo, mesh_hi, n, sc.blo, sc.bhi, sc.bounds);
 }
 
 static void sort_passes(cudaStream_t s, uint32_t n, BuildScratch& sc) {
@@ -773,6 +814,7 @@ cudaError_t launch_build_wide(cudaStream_t s, uint32_t n, WideNode* nodes, uint3
   ep.nodes = nodes, ep.node_base = node_base, ep.prim_base = prim_base;
   ep.root_of = sc.root_of, ep.counters = sc.counters;
   ep.v = payload.vertices, ep.idx = payload.indices, ep.tris = payload.tris, ep.leaf_inst = payload.leaf_inst;
+  ep.soup = payload.soup, ep.prim_ids = payload.prim_ids;
   ep.out_lo = root_lo, ep.out_hi = root_hi, ep.result = result;
   void* eargs[] = {&ep};
   return cudaLaunchCooperativeKernel((const void*)k_emit_wide, dim3(grid), dim3(kThreads), eargs, 0, s);

@@ -34,8 +34,10 @@ struct BuildScratch {
 struct PrimPayload {
   const AsunaVertex* vertices = nullptr;
   const uint32_t* indices = nullptr;
-  TriSlot* tris = nullptr;        // absolute array
-  uint32_t* leaf_inst = nullptr;  // absolute array
+  const TriSlot* soup = nullptr;       // world-space triangles (merged BLAS): primitive i = soup[i], vertices/indices unused
+  const uint32_t* prim_ids = nullptr;  // top level: primitive -> instance index (nullptr = identity)
+  TriSlot* tris = nullptr;             // absolute array
+  uint32_t* leaf_inst = nullptr;       // absolute array
 };
 
 struct BuildResult {  // written by the emit kernel, read back once after all builds
@@ -46,8 +48,10 @@ struct BuildResult {  // written by the emit kernel, read back once after all bu
 };
 
 void launch_tri_boxes(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, BuildScratch& sc);
-void launch_instance_boxes(cudaStream_t s, const DInstance* inst, const float4* mesh_lo, const float4* mesh_hi,
-                           uint32_t n, BuildScratch& sc);
+void launch_world_triangles(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, const float4 o2w[3],
+                            uint32_t inst, TriSlot* soup, uint32_t offset, bool first, BuildScratch& sc);
+void launch_instance_boxes(cudaStream_t s, const DInstance* inst, const uint32_t* ids, const float4* mesh_lo,
+                           const float4* mesh_hi, uint32_t n, BuildScratch& sc);
 cudaError_t launch_build_wide(cudaStream_t s, uint32_t n, WideNode* nodes, uint32_t node_base, uint32_t prim_base,
                               BuildScratch& sc, const PrimPayload& payload, float cost_prim, float4* root_lo,
                               float4* root_hi, BuildResult* result);

@@ -44,7 +44,7 @@ constexpr int kMaxLeafPrims = 3;
 // Triangle slot in BVH-leaf order: three float4 (48 B), prim id in v0.w.
 struct __align__(16) TriSlot {
   float4 v0;  // xyz, w = __uint_as_float(primitive id in the mesh)
-  float4 v1;
+  float4 v1;  // xyz, w = __uint_as_float(instance id) in the world BLAS, unused in a mesh BLAS
   float4 v2;
 };
 
@@ -85,6 +85,8 @@ struct SceneView {
   const DTexture* textures;
   DTexture env[3];                // env, marginal, conditional
   uint32_t n_instances;
+  uint32_t world_inst;            // pseudo-instance of the merged world-space BLAS (hits take their instance id from the triangle), or ~0
+  uint32_t single_root;           // every instance merged: root of the world BLAS, traversal is single-level; else ~0
   uint32_t magic;                 // 0x4B000000 from the constant bank: keeps the PRMT selectors immediate (traverse.cuh)
   uint32_t refill_lanes;          // traversal tuning (ASUNA_TUNE): refill when this many lanes are idle
   uint32_t tri_vote_shift;        // triangle step quorum = live lanes >> shift

@@ -83,25 +83,26 @@ struct UserPolicy {  // asuna_trace_rays / asuna_occlusion_rays / asuna_trace_pr
   }
 };
 
-template <bool COUNT>
+template <bool COUNT, bool SINGLE>
 __global__ void __launch_bounds__(kTraceThreads, ASUNA_TRACE_MIN_BLOCKS)
 k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter, int qsel) {
   ClosestPolicy pol{ps, ps.queue[qsel], sc.instances};
-  trace_persistent<false, COUNT>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow,
+  trace_persistent<false, COUNT, SINGLE>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow,
                                  &cnt->node_visits, &cnt->tri_tests);
 }
 
+template <bool SINGLE>
 __global__ void __launch_bounds__(kTraceThreads, ASUNA_TRACE_MIN_BLOCKS)
 k_trace_shadow(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter) {
   ShadowPolicy pol{ps};
-  trace_persistent<true, false>(sc, pol, cnt->shadow[iter], &cnt->ticket_shadow[iter], &cnt->stack_overflow, nullptr,
+  trace_persistent<true, false, SINGLE>(sc, pol, cnt->shadow[iter], &cnt->ticket_shadow[iter], &cnt->stack_overflow, nullptr,
                                 nullptr);
 }
 
-template <bool ANY>
+template <bool ANY, bool SINGLE>
 __global__ void __launch_bounds__(kTraceThreads)
 k_trace_user(const __grid_constant__ SceneView sc, UserPolicy pol, uint32_t n, uint32_t* ticket, Counters* cnt) {
-  trace_persistent<ANY, false>(sc, pol, n, ticket, &cnt->stack_overflow, nullptr, nullptr);
+  trace_persistent<ANY, false, SINGLE>(sc, pol, n, ticket, &cnt->stack_overflow, nullptr, nullptr);
 }
 
 // Adds one batch's per-iteration counters into the persistent totals (one thread; a few hundred words).
@@ -433,8 +434,14 @@ void launch_raygen(cudaStream_t s, const FrameParams& fp, const PathState& ps, c
 }
 void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
                           int iter, int qsel, bool counting) {
-  if (counting) k_trace_closest<true><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
-  else k_trace_closest<false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+  const bool single = sc.single_root != 0xFFFFFFFFu;  // every instance merged into the world BLAS: no instance level
+  if (counting) {
+    if (single) k_trace_closest<true, true><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+    else k_trace_closest<true, false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+  } else {
+    if (single) k_trace_closest<false, true><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+    else k_trace_closest<false, false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+  }
 }
 void launch_fold_counters(cudaStream_t s, const Counters* cnt, Totals* tot, int iters) {
   k_fold_counters<<<1, 1, 0, s>>>(cnt, tot, iters);
@@ -475,7 +482,8 @@ int launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, cons
 }
 void launch_trace_shadow(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
                          int iter) {
-  k_trace_shadow<<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
+  if (sc.single_root != 0xFFFFFFFFu) k_trace_shadow<true><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
+  else k_trace_shadow<false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
 }
 void launch_accumulate(cudaStream_t s, const FrameParams& fp, const PathState& ps, const OutputImages& out) {
   k_accumulate<<<div_up(fp.n_pixels, 256), 256, 0, s>>>(fp, ps, out);
@@ -496,8 +504,14 @@ void launch_trace_user(cudaStream_t s, const LaunchDims& ld, const SceneView& sc
   cudaMemsetAsync(ticket, 0, sizeof(uint32_t), s);
   UserPolicy pol{rays, tuv, inst_prim, occluded};
   uint32_t blocks = std::min(ld.trace_blocks, std::max(1u, div_up(n, kTraceThreads)));
-  if (occluded) k_trace_user<true><<<blocks, kTraceThreads, 0, s>>>(sc, pol, n, ticket, cnt);
-  else k_trace_user<false><<<blocks, kTraceThreads, 0, s>>>(sc, pol, n, ticket, cnt);
+  const bool single = sc.single_root != 0xFFFFFFFFu;
+  if (occluded) {
+    if (single) k_trace_user<true, true><<<blocks, kTraceThreads, 0, s>>>(sc, pol, n, ticket, cnt);
+    else k_trace_user<true, false><<<blocks, kTraceThreads, 0, s>>>(sc, pol, n, ticket, cnt);
+  } else {
+    if (single) k_trace_user<false, true><<<blocks, kTraceThreads, 0, s>>>(sc, pol, n, ticket, cnt);
+    else k_trace_user<false, false><<<blocks, kTraceThreads, 0, s>>>(sc, pol, n, ticket, cnt);
+  }
 }
 
 template <uint32_t... K>
@@ -515,7 +529,7 @@ static cudaError_t shade_occupancy(LaunchDims& ld, int sm_count, std::integer_se
 
 cudaError_t query_launch_dims(LaunchDims& ld, int sm_count) {
   int per_sm = 0;
-  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest<false>, kTraceThreads, 0);
+  cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest<false, false>, kTraceThreads, 0);
   if (e != cudaSuccess) return e;
   ld.trace_blocks = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
   return shade_occupancy(ld, sm_count, std::make_integer_sequence<uint32_t, kNumKinds>{});

@@ -48,7 +48,9 @@ struct RaySpace {  // ray constants in the space being traversed (world or one i
 ADEV void setup_space(RaySpace& r, float3 o, float3 d) {
   r.o = o;
   r.idir = f3(safe_rcp(d.x), safe_rcp(d.y), safe_rcp(d.z));
-  r.oct = (r.idir.x < 0.f ? 1u : 0u) | (r.idir.y < 0.f ? 2u : 0u) | (r.idir.z < 0.f ? 4u : 0u);
+  // sign bits of the direction (rcp keeps them): three shifts instead of three compare/select pairs
+  r.oct = (__float_as_uint(r.idir.x) >> 31) | ((__float_as_uint(r.idir.y) >> 31) << 1) |
+          ((__float_as_uint(r.idir.z) >> 31) << 2);
 }
 // kz = dominant axis of d, kx = kz+1, ky = kz+2 (cyclic).  The kx/ky swap of the paper only flips the sign of
 // all three edge functions together (exactly, in floating point), which changes no result without culling.
@@ -168,13 +170,17 @@ struct Lane {  // (the stack itself is a separate local array so that these stay
   bool shear_ok;  // the watertight-test constants of the current instance are computed at its first triangle
 };
 
-ADEV void lane_begin(Lane& L, float3 o, float3 d, float tmin, float tmax) {
+// SINGLE = every instance lives in the merged world-space BLAS (SceneView::single_root): there is no instance
+// level, the ray stays in world space and the instance id of a hit comes from its triangle slot.
+template <bool SINGLE>
+ADEV void lane_begin(Lane& L, const SceneView& sc, float3 o, float3 d, float tmin, float tmax) {
   L.sp = 0, L.blas_sp = 0;
-  L.ng = make_uint2(0u, 0x80000000u);  // the instance-level root
+  L.ng = make_uint2(SINGLE ? sc.single_root : 0u, 0x80000000u);  // the root (instance level unless SINGLE)
   L.tg = make_uint2(0u, 0u);
   L.wo = o, L.wd = d, L.tmin = tmin, L.tmax = tmax;
   setup_space(L.rs, o, d);
-  L.in_blas = false, L.found = false, L.shear_ok = false;
+  L.in_blas = SINGLE, L.found = false, L.shear_ok = SINGLE;
+  if (SINGLE) setup_shear(L.rs, d);
   L.cur_inst = 0;
   L.best.inst = 0xFFFFFFFFu, L.best.prim = 0xFFFFFFFFu, L.best.b1 = L.best.b2 = L.best.t = 0.f;
 }
@@ -185,7 +191,7 @@ ADEV void lane_push(Lane& L, uint2* stack, uint2 e, uint32_t* overflow) {
 }
 
 // One wide-node step: take the nearest pending child of the current node group, test its eight children.
-template <bool COUNT>
+template <bool COUNT, bool SINGLE>
 ADEV void lane_node_step(Lane& L, uint2* stack, const SceneView& sc, uint32_t* overflow, uint32_t& n_nodes) {
   const uint32_t hits = L.ng.y;
   const uint32_t bit = 31u - (uint32_t)__clz(hits);
@@ -193,7 +199,7 @@ ADEV void lane_node_step(Lane& L, uint2* stack, const SceneView& sc, uint32_t* o
   const uint32_t octinv = 7u ^ L.rs.oct;
   const uint32_t slot = (bit - 24u) ^ octinv;
   const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
-  const WideNode* nodes = L.in_blas ? sc.blas_nodes : sc.tlas_nodes;
+  const WideNode* nodes = (SINGLE || L.in_blas) ? sc.blas_nodes : sc.tlas_nodes;
   const uint4* np = reinterpret_cast<const uint4*>(nodes + L.ng.x + rel);
   const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
   if (COUNT) n_nodes++;
@@ -238,7 +244,7 @@ ADEV void lane_enter_instance(Lane& L, uint2* stack, const SceneView& sc, uint32
 }
 
 // One triangle of the current primitive group.  Returns true when the hit ends an any-hit query.
-template <bool ANY, bool COUNT>
+template <bool ANY, bool COUNT, bool SINGLE>
 ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
   const uint32_t k = (uint32_t)__ffs((int)L.tg.y) - 1u;
   L.tg.y &= L.tg.y - 1u;
@@ -246,7 +252,7 @@ ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
   float4 v0 = __ldg(&tp->v0), v1 = __ldg(&tp->v1), v2 = __ldg(&tp->v2);
   float t, b1, b2;
   if (COUNT) n_tris++;
-  if (!L.shear_ok) {  // many instance visits never reach a triangle: the three IEEE divisions are paid only here
+  if (!SINGLE && !L.shear_ok) {  // many instance visits never reach a triangle: the three IEEE divisions are paid only here
     const DInstance* in = sc.instances + L.cur_inst;
     float4 m[3] = {__ldg(&in->w2o[0]), __ldg(&in->w2o[1]), __ldg(&in->w2o[2])};
     setup_shear(L.rs, xf_vector(m, L.wd));
@@ -254,18 +260,19 @@ ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
   }
   if (!hit_triangle(L.rs, f3(v0), f3(v1), f3(v2), t, b1, b2)) return false;
   if (!(t > L.tmin)) return false;
-  uint32_t prim = __float_as_uint(v0.w);
+  const uint32_t prim = __float_as_uint(v0.w);
+  const uint32_t inst = (SINGLE || L.cur_inst == sc.world_inst) ? __float_as_uint(v1.w) : L.cur_inst;
   bool closer = t < L.tmax || (t == L.tmax && L.found &&
-                               (L.cur_inst < L.best.inst || (L.cur_inst == L.best.inst && prim < L.best.prim)));
+                               (inst < L.best.inst || (inst == L.best.inst && prim < L.best.prim)));
   if (!closer) return false;
-  L.best.t = t, L.best.b1 = b1, L.best.b2 = b2, L.best.inst = L.cur_inst, L.best.prim = prim;
+  L.best.t = t, L.best.b1 = b1, L.best.b2 = b2, L.best.inst = inst, L.best.prim = prim;
   L.tmax = t;
   L.found = true;
   return ANY;
 }
 
 // Persistent warp loop.  Policy: load(i, o, d, tmin, tmax) reads ray i; commit(i, found, hit) stores its result.
-template <bool ANY, bool COUNT, class Policy>
+template <bool ANY, bool COUNT, bool SINGLE, class Policy>
 __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t count, uint32_t* ticket, uint32_t* overflow,
                                  unsigned long long* node_visits, unsigned long long* tri_tests) {
   const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
@@ -280,7 +287,7 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
       float3 o, d;
       float t0, t1;
       pol.load(i, o, d, t0, t1);
-      lane_begin(L, o, d, t0, t1);
+      lane_begin<SINGLE>(L, sc, o, d, t0, t1);
       pol.commit(i, false, L.best);
     }
     return;
@@ -299,7 +306,7 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
           float3 o, d;
           float t0, t1;
           pol.load(i, o, d, t0, t1);
-          lane_begin(L, o, d, t0, t1);
+          lane_begin<SINGLE>(L, sc, o, d, t0, t1);
           ray = i;
           active = true;
         }
@@ -313,7 +320,7 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
       // node group of their own mesh-level stack and keep traversing
       if (active && L.ng.y <= 0x00FFFFFFu) {
         if (L.tg.y == 0u) {
-          if (L.in_blas && L.sp == L.blas_sp) {
+          if (!SINGLE && L.in_blas && L.sp == L.blas_sp) {
             L.in_blas = false;
             setup_space(L.rs, L.wo, L.wd);
           }
@@ -325,21 +332,21 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
             if (e.y > 0x00FFFFFFu) L.ng = e;
             else L.tg = e;
           }
-        } else if (L.in_blas && L.sp > L.blas_sp && stack[L.sp - 1].y > 0x00FFFFFFu) {
+        } else if ((SINGLE || L.in_blas) && L.sp > (SINGLE ? 0 : L.blas_sp) && stack[L.sp - 1].y > 0x00FFFFFFu) {
           const uint2 e = stack[L.sp - 1];
           stack[L.sp - 1] = L.tg;
           L.ng = e;
           L.tg = make_uint2(0u, 0u);
         }
       }
-      if (active && L.ng.y > 0x00FFFFFFu) lane_node_step<COUNT>(L, stack, sc, overflow, n_nodes);
-      if (active && !L.in_blas && L.tg.y) lane_enter_instance(L, stack, sc, overflow);
-      const bool want_tri = active && L.in_blas && L.tg.y != 0u;
+      if (active && L.ng.y > 0x00FFFFFFu) lane_node_step<COUNT, SINGLE>(L, stack, sc, overflow, n_nodes);
+      if (!SINGLE && active && !L.in_blas && L.tg.y) lane_enter_instance(L, stack, sc, overflow);
+      const bool want_tri = active && (SINGLE || L.in_blas) && L.tg.y != 0u;
       const uint32_t m_tri = __ballot_sync(0xFFFFFFFFu, want_tri);
       const uint32_t m_node = __ballot_sync(0xFFFFFFFFu, active && L.ng.y > 0x00FFFFFFu);
       const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, active);
       if (m_tri && (m_node == 0u || __popc(m_tri) >= (__popc(m_act) >> sc.tri_vote_shift))) {
-        if (want_tri && lane_triangle_step<ANY, COUNT>(L, sc, n_tris)) {
+        if (want_tri && lane_triangle_step<ANY, COUNT, SINGLE>(L, sc, n_tris)) {
           pol.commit(ray, true, L.best);
           active = false;
         }
