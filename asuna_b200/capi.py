@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "abi_sizes", "create", "destroy", "last_error", "set_film", "add_texture", "set_envmap", "add_mesh",
     "add_material", "set_lights", "add_instance", "build_accel", "set_camera", "set_sunsky", "set_state",
     "reset_frame", "render_frames", "set_partition", "sync", "read_channel", "export_partial",
-    "import_partial", "channel_device_ptr", "stream_handle", "set_counting", "get_stats", "reset_stats", "trace_primary", "trace_rays",
+    "import_partial", "host_alloc", "host_free", "channel_device_ptr", "stream_handle", "set_counting", "get_stats", "reset_stats", "trace_primary", "trace_rays",
     "occlusion_rays", "accel_stats")
 
 
@@ -76,9 +76,13 @@ class Context:
             self.h = C.c_void_p()
             raise AsunaError(f"{self.L.prefix}create failed with {rc} (no CUDA device?)")
         self.width = self.height = 0
+        self._pinned = []
 
     def close(self):
         if self.h:
+            for p in self._pinned:
+                self.L.fn("host_free")(self.h, p)
+            self._pinned = []
             self.L.fn("destroy", None)(self.h)
             self.h = C.c_void_p()
 
@@ -157,10 +161,21 @@ class Context:
     def sync(self):
         return self._call("sync")
 
-    def read_channel(self, ch):
-        out = np.empty((self.height, self.width, 4), np.float32)
+    def read_channel(self, ch, out=None):
+        """Image `ch` as (h, w, 4) float32.  `out` (e.g. from pinned_image()) is filled in place when given."""
+        if out is None:
+            out = np.empty((self.height, self.width, 4), np.float32)
+        assert out.dtype == np.float32 and out.size == self.height * self.width * 4 and out.flags.c_contiguous
         self._call("read_channel", C.c_int(ch), _ptr(out))
         return out
+
+    def pinned_image(self):
+        """A page-locked (h, w, 4) float32 array owned by the library (asuna_host_alloc); freed with the context."""
+        n = self.height * self.width * 4
+        p = C.c_void_p()
+        self._call("host_alloc", C.c_size_t(n * 4), C.byref(p))
+        self._pinned.append(p)
+        return np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(n,)).reshape(self.height, self.width, 4)
 
     def export_partial(self):
         p = C.c_void_p()

@@ -771,6 +771,18 @@ int asuna_read_channel(asuna_ctx* ctx, int ch, float* out) {
   return 0;
 }
 
+int asuna_host_alloc(asuna_ctx* ctx, size_t bytes, void** out) {
+  if (!out || bytes == 0) return fail(ctx, ASUNA_E_INVALID, "bad host allocation request");
+  cudaSetDevice(ctx->device);
+  ASUNA_CUDA_CHECK(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+  return 0;
+}
+int asuna_host_free(asuna_ctx* ctx, void* p) {
+  if (!p) return 0;
+  ASUNA_CUDA_CHECK(cudaFreeHost(p));
+  return 0;
+}
+
 int asuna_export_partial(asuna_ctx* ctx, void** out) {
   if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
   cudaSetDevice(ctx->device);

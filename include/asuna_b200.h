@@ -18,6 +18,7 @@
 #ifndef ASUNA_B200_H
 #define ASUNA_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -248,6 +249,12 @@ int asuna_sync(asuna_ctx* ctx);
 /* ≙ vkTextureToBuffer + map, reference src/tracer/tracer.cpp:313-342,365.
  * channel 0 = radiance mean, 1..7 = AOVs (frame 0), 8 = filter-weight sum.  w*h*4 floats. */
 int asuna_read_channel(asuna_ctx* ctx, int channel, float* rgba32f_out);
+
+/* Page-locked host memory for the read-back / upload buffers of a caller (≙ the host-visible, host-coherent
+ * staging buffer the reference maps in src/tracer/tracer.cpp:317-336): asuna_read_channel into such a buffer is
+ * one DMA, into pageable memory the driver stages it.  Free with asuna_host_free. */
+int asuna_host_alloc(asuna_ctx* ctx, size_t bytes, void** out_host_ptr);
+int asuna_host_free(asuna_ctx* ctx, void* host_ptr);
 
 /* Multi-GPU combine.  export: writes (sum_w*L.rgb, sum_w) per pixel into a device buffer
  * owned by the library and returns its device pointer (w*h*4 floats) for the caller's

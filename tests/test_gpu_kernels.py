@@ -65,11 +65,49 @@ def _random_rays(sc, n, seed):
     return rays
 
 
-@pytest.mark.parametrize("builder", [
-    lambda: scenes.cornell_materials(32, 32, env=False, lights="all"),
-    lambda: scenes.instanced_field(32, 32, subdiv=3, grid=5),
+def _mixed_scene():
+    """An instanced mesh next to several single-use meshes: the world BLAS (flattened singles) and per-mesh
+    BLASes meet under one top level."""
+    sc = scenes.instanced_field(32, 32, subdiv=3, grid=4)
+    v, idx = scenes.blob(3, 5, 0.3)
+    sc.add_mesh("solo", v, idx)
+    sc.add_instance("solo", "lam", scenes.translation((0.3, 3.0, 0.2)) @ scenes.rotation_y(0.7) @ scenes.scaling((1.5, 0.8, 1.2)))
+    return sc
+
+
+SCENE_BUILDERS = [
+    lambda: scenes.cornell_materials(32, 32, env=False, lights="all"),  # all single-use: single-level traversal
+    lambda: scenes.instanced_field(32, 32, subdiv=3, grid=5),           # instanced + one single: plain two-level
     lambda: scenes.glass_blob(32, 32, subdiv=5, env_size=(16, 8)),
-])
+    _mixed_scene,                                                       # instanced + world BLAS
+]
+
+
+@pytest.mark.parametrize("builder", SCENE_BUILDERS)
+def test_flattening_does_not_change_hits(product_lib, builder, monkeypatch):
+    """Single-use instances are pre-transformed into one world-space BLAS (api.cu); against the plain two-level
+    structure (ASUNA_FLATTEN=0) the nearest hits must be the same primitives at the same distance."""
+    from asuna_b200 import capi
+    sc = builder()
+    rays = _random_rays(sc, 100000, 9)
+    out = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("ASUNA_FLATTEN", flag)
+        ctx = capi.Context(product_lib, 0)
+        sc.upload(ctx)
+        out.append(ctx.trace_rays(rays) + (ctx.occlusion_rays(rays),))
+        ctx.close()
+    (t0, i0, o0), (t1, i1, o1) = out
+    same = (i0 == i1).all(axis=1)
+    tie = ~same & (np.abs(t0[:, 0] - t1[:, 0]) <= 1e-5 * np.maximum(1.0, np.abs(t0[:, 0])))
+    assert (same | tie).mean() >= 0.9995, (same.mean(), tie.mean())
+    hit = same & (i0[:, 0] != 0xFFFFFFFF)
+    assert hit.mean() > 0.2
+    assert (np.abs(t0[hit, 0] - t1[hit, 0]) / np.maximum(1.0, t0[hit, 0])).max() <= 1e-5
+    assert (o0 == o1).mean() >= 0.9995
+
+
+@pytest.mark.parametrize("builder", SCENE_BUILDERS)
 def test_traversal_matches_oracle_on_random_rays(gpu_ctx, cpu_ctx, builder):
     sc = builder()
     sc.upload(gpu_ctx)
