@@ -33,13 +33,14 @@ struct ClosestPolicy {  // rgen:108-109: tmin 1e-5, tmax 1e10; the hit record go
   PathState ps;
   const uint32_t* queue;
   const DInstance* instances;
-  ADEV void load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
+  ADEV uint32_t load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
     const uint32_t slot = queue[i];
     o = f3(ps.ray_o[slot]), d = f3(ps.ray_d[slot]);
     tmin = kMinimum, tmax = kInfinity;
+    return slot;
   }
-  ADEV void commit(uint32_t i, bool, const HitRec& h) const {
-    ps.hit[queue[i]] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), h.inst, h.prim);
+  ADEV void commit(uint32_t i, uint32_t slot, bool, const HitRec& h) const {
+    ps.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), h.inst, h.prim);
     uint32_t kind = kKindMiss;  // the key the hit queue is regrouped by before shading
     if (h.inst != 0xFFFFFFFFu) {
       const uint32_t mt = __ldg(&instances[h.inst].mat_type);
@@ -51,12 +52,13 @@ struct ClosestPolicy {  // rgen:108-109: tmin 1e-5, tmax 1e10; the hit record go
 
 struct ShadowPolicy {  // rgen:117-125: tmin 0, tmax = dist - 2 EPS, first hit ends it; unoccluded adds dRec.radiance
   PathState ps;
-  ADEV void load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
+  ADEV uint32_t load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
     const float4 a = ps.sh_o[i];
     o = f3(a), d = f3(ps.sh_d[i]);
     tmin = 0.0f, tmax = a.w;
+    return 0u;
   }
-  ADEV void commit(uint32_t i, bool occluded, const HitRec&) const {
+  ADEV void commit(uint32_t i, uint32_t, bool occluded, const HitRec&) const {
     if (occluded) return;
     const uint32_t slot = __float_as_uint(ps.sh_d[i].w);
     const float4 L = ps.sh_l[i], r = ps.rad[slot];
@@ -69,11 +71,12 @@ struct UserPolicy {  // asuna_trace_rays / asuna_occlusion_rays / asuna_trace_pr
   float* tuv;
   uint32_t* inst_prim;
   uint8_t* occluded;
-  ADEV void load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
+  ADEV uint32_t load(uint32_t i, float3& o, float3& d, float& tmin, float& tmax) const {
     const float4 a = rays[2 * i], b = rays[2 * i + 1];
     o = f3(a), d = f3(b), tmin = a.w, tmax = b.w;
+    return 0u;
   }
-  ADEV void commit(uint32_t i, bool found, const HitRec& h) const {
+  ADEV void commit(uint32_t i, uint32_t, bool found, const HitRec& h) const {
     if (occluded) {
       occluded[i] = found ? 1 : 0;
       return;

@@ -108,10 +108,18 @@ ADEV float magic_byte(uint32_t v, uint32_t magic) {
 // Slab test of the eight quantised child boxes of one compressed wide node (Ylitie et al. 2017, section 3).
 // Plane t = q * a + b with a = 2^e / d, b = (p - o) / d; q arrives as 2^23 + q, so b is pre-biased by
 // -2^23 a, whose rounding error (<= |a| / 2, half a quantisation step) is covered by moving the near planes
-// half a step down and the far planes half a step up.  The far side is also widened by 2 ulp so that a box never
-// rejects what the watertight triangle test accepts.  Returns bit s = child in slot s hit.
-ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n2, uint4 n3, uint4 n4, const RaySpace& r, float tmin, float tmax,
-                                  uint32_t magic) {
+// half a step down and the far planes half a step up.  The exit distance is also widened by ~3 ulp so that a box
+// never rejects what the watertight triangle test accepts.
+//
+// Returns the hit mask of the node in stack-entry form: bit 24 + (slot ^ octinv) for a hit inner child (so that the
+// highest set bit is the child nearest along the ray's octant), bits [offset, offset + count) of the primitive
+// slots of a hit leaf child.  Both come from the meta byte (count/"1" in its top 3 bits, offset/"24 + slot" in
+// its low 5) handled four children at a time, as in the paper's listing.
+template <int J>
+ADEV uint32_t byte_of(uint32_t x) { return __byte_perm(x, 0u, 0x4440 + J); }
+
+ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 n4, const RaySpace& r, float tmin,
+                                  float tmax, uint32_t magic) {
   const float kBias = 8388608.0f, kWiden = 1.0000004f;
   const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * r.idir.x;
   const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * r.idir.y;
@@ -121,12 +129,18 @@ ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n2, uint4 n3, uint4 n4, const 
   const float bz = fmaf(-kBias, az, (__uint_as_float(n0.z) - r.o.z) * r.idir.z);
   const float hx = 0.50001f * fabsf(ax), hy = 0.50001f * fabsf(ay), hz = 0.50001f * fabsf(az);
   const float bnx = bx - hx, bny = by - hy, bnz = bz - hz;
-  const float afx = ax * kWiden, afy = ay * kWiden, afz = az * kWiden;
-  const float bfx = (bx + hx) * kWiden, bfy = (by + hy) * kWiden, bfz = (bz + hz) * kWiden;
+  const float bfx = bx + hx, bfy = by + hy, bfz = bz + hz;
   const bool nx = (r.oct & 1u) != 0u, ny = (r.oct & 2u) != 0u, nz = (r.oct & 4u) != 0u;
-  uint32_t hit8 = 0;
+  const uint32_t octinv4 = (7u ^ r.oct) * 0x01010101u;
+  uint32_t mask = 0;
 #pragma unroll
   for (int h = 0; h < 2; h++) {
+    const uint32_t meta4 = h ? n1.w : n1.z;
+    const uint32_t is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;  // offsets >= 24 mark inner children
+    uint32_t inner_mask4;                                             // 0xFF in the bytes of inner children
+    asm("prmt.b32 %0, %1, %2, 0xba98;" : "=r"(inner_mask4) : "r"(is_inner4 << 3), "r"(0u));
+    const uint32_t bit_index4 = (meta4 ^ (octinv4 & inner_mask4)) & 0x1F1F1F1Fu;
+    const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
     const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
     const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
@@ -134,39 +148,33 @@ ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n2, uint4 n3, uint4 n4, const 
     const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
 #define ASUNA_CHILD(J)                                                                                      \
     {                                                                                                         \
-      float tnx = fmaf(magic_byte<J>(nearx, magic), ax, bnx), tfx = fmaf(magic_byte<J>(farx, magic), afx, bfx); \
-      float tny = fmaf(magic_byte<J>(neary, magic), ay, bny), tfy = fmaf(magic_byte<J>(fary, magic), afy, bfy); \
-      float tnz = fmaf(magic_byte<J>(nearz, magic), az, bnz), tfz = fmaf(magic_byte<J>(farz, magic), afz, bfz); \
+      float tnx = fmaf(magic_byte<J>(nearx, magic), ax, bnx), tfx = fmaf(magic_byte<J>(farx, magic), ax, bfx); \
+      float tny = fmaf(magic_byte<J>(neary, magic), ay, bny), tfy = fmaf(magic_byte<J>(fary, magic), ay, bfy); \
+      float tnz = fmaf(magic_byte<J>(nearz, magic), az, bnz), tfz = fmaf(magic_byte<J>(farz, magic), az, bfz); \
       float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                  \
-      float cmax = fminf(fminf(tfx, tfy), fminf(tfz, tmax));                                                  \
-      if (cmin <= cmax) hit8 |= 1u << (4 * h + J);                                                            \
+      float cmax = fminf(fminf(fminf(tfx, tfy), tfz) * kWiden, tmax);                                         \
+      if (cmin <= cmax) mask |= byte_of<J>(child_bits4) << byte_of<J>(bit_index4);                            \
     }
     ASUNA_CHILD(0) ASUNA_CHILD(1) ASUNA_CHILD(2) ASUNA_CHILD(3)
 #undef ASUNA_CHILD
   }
-  return hit8;
-}
-
-// bit s -> bit (s ^ c): three conditional swaps of adjacent bits / pairs / nibbles
-ADEV uint32_t xor_permute8(uint32_t x, uint32_t c) {
-  if (c & 1u) x = ((x & 0x55u) << 1) | ((x >> 1) & 0x55u);
-  if (c & 2u) x = ((x & 0x33u) << 2) | ((x >> 2) & 0x33u);
-  if (c & 4u) x = ((x & 0x0Fu) << 4) | ((x >> 4) & 0x0Fu);
-  return x;
+  return mask;
 }
 
 // Per-lane traversal state.  Stack entries are (base index, mask) groups: mask > 0x00FFFFFF = a node group
 // (hit bits of inner children in the top byte, already in visiting order: highest bit = nearest octant; imask in
-// the low byte), otherwise a primitive group (<= 24 hit bits of consecutive primitive slots).
-struct Lane {  // (the stack itself is a separate local array so that these stay in registers)
+// the low byte), otherwise a primitive group (<= 24 hit bits of consecutive primitive slots).  The newest stack
+// entry lives in registers (`top`); local memory holds the ones below it, so the common pop / peek / swap of the
+// postponing logic never waits on a load.
+struct Lane {
   int sp, blas_sp;
-  uint2 ng, tg;
+  uint2 ng, tg, top;
   RaySpace rs;
   float3 wo, wd;
   float tmin, tmax;
-  HitRec best;
+  HitRec best;  // best.inst == ~0: nothing found yet
   uint32_t cur_inst;
-  bool in_blas, found;
+  bool in_blas;
   bool shear_ok;  // the watertight-test constants of the current instance are computed at its first triangle
 };
 
@@ -179,15 +187,25 @@ ADEV void lane_begin(Lane& L, const SceneView& sc, float3 o, float3 d, float tmi
   L.tg = make_uint2(0u, 0u);
   L.wo = o, L.wd = d, L.tmin = tmin, L.tmax = tmax;
   setup_space(L.rs, o, d);
-  L.in_blas = SINGLE, L.found = false, L.shear_ok = SINGLE;
+  L.in_blas = SINGLE, L.shear_ok = SINGLE;
   if (SINGLE) setup_shear(L.rs, d);
   L.cur_inst = 0;
   L.best.inst = 0xFFFFFFFFu, L.best.prim = 0xFFFFFFFFu, L.best.b1 = L.best.b2 = L.best.t = 0.f;
 }
 
+// stack[k] holds entry k - 1 (slot 0 is a dummy), so push and pop need no "is there an entry below" branch
 ADEV void lane_push(Lane& L, uint2* stack, uint2 e, uint32_t* overflow) {
-  if (L.sp < kStackSize) stack[L.sp++] = e;
-  else atomicAdd(overflow, 1u);
+  if (L.sp < kStackSize) {
+    stack[L.sp++] = L.top;
+    L.top = e;
+  } else {
+    atomicAdd(overflow, 1u);
+  }
+}
+ADEV uint2 lane_pop(Lane& L, const uint2* stack) {
+  const uint2 e = L.top;
+  L.top = stack[--L.sp];
+  return e;
 }
 
 // One wide-node step: take the nearest pending child of the current node group, test its eight children.
@@ -196,27 +214,18 @@ ADEV void lane_node_step(Lane& L, uint2* stack, const SceneView& sc, uint32_t* o
   const uint32_t hits = L.ng.y;
   const uint32_t bit = 31u - (uint32_t)__clz(hits);
   uint2 rest = make_uint2(L.ng.x, hits & ~(1u << bit));
-  const uint32_t octinv = 7u ^ L.rs.oct;
-  const uint32_t slot = (bit - 24u) ^ octinv;
+  const uint32_t slot = (bit - 24u) ^ 7u ^ L.rs.oct;
   const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
   const WideNode* nodes = (SINGLE || L.in_blas) ? sc.blas_nodes : sc.tlas_nodes;
   const uint4* np = reinterpret_cast<const uint4*>(nodes + L.ng.x + rel);
   const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
   if (COUNT) n_nodes++;
   if (rest.y > 0x00FFFFFFu) lane_push(L, stack, rest, overflow);
-  const uint32_t hit8 = intersect_wide_node(n0, n2, n3, n4, L.rs, L.tmin, L.tmax, sc.magic);
-  const uint32_t imask = n0.w >> 24;
-  L.ng = make_uint2(n1.x, (xor_permute8(hit8 & imask, octinv) << 24) | imask);
-  uint32_t leaf = hit8 & ~imask, prims = 0;
-  while (leaf) {  // leaf children hit: their primitive bits (unary count << offset)
-    const uint32_t j = (uint32_t)__ffs((int)leaf) - 1u;
-    leaf &= leaf - 1u;
-    const uint32_t m = ((j & 4u) ? n1.w : n1.z) >> (8u * (j & 3u)) & 0xFFu;
-    prims |= (m >> 5) << (m & 31u);
-  }
-  if (prims) {
+  const uint32_t mask = intersect_wide_node(n0, n1, n2, n3, n4, L.rs, L.tmin, L.tmax, sc.magic);
+  L.ng = make_uint2(n1.x, (mask & 0xFF000000u) | (n0.w >> 24));
+  if (mask & 0x00FFFFFFu) {
     if (L.tg.y) lane_push(L, stack, L.tg, overflow);  // an older postponed group goes under the newer, nearer one
-    L.tg = make_uint2(n1.y, prims);
+    L.tg = make_uint2(n1.y, mask & 0x00FFFFFFu);
   }
 }
 
@@ -229,8 +238,8 @@ ADEV void lane_enter_instance(Lane& L, uint2* stack, const SceneView& sc, uint32
     L.tg.y = 0;
     return;
   }
-  if (L.tg.y) stack[L.sp++] = L.tg;
-  if (L.ng.y > 0x00FFFFFFu) stack[L.sp++] = L.ng;
+  if (L.tg.y) lane_push(L, stack, L.tg, overflow);
+  if (L.ng.y > 0x00FFFFFFu) lane_push(L, stack, L.ng, overflow);
   L.cur_inst = __ldg(&sc.tlas_leaf_inst[L.tg.x + k]);
   const DInstance* in = sc.instances + L.cur_inst;
   float4 r0 = __ldg(&in->w2o[0]), r1 = __ldg(&in->w2o[1]), r2 = __ldg(&in->w2o[2]);
@@ -262,56 +271,70 @@ ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
   if (!(t > L.tmin)) return false;
   const uint32_t prim = __float_as_uint(v0.w);
   const uint32_t inst = (SINGLE || L.cur_inst == sc.world_inst) ? __float_as_uint(v1.w) : L.cur_inst;
-  bool closer = t < L.tmax || (t == L.tmax && L.found &&
+  bool closer = t < L.tmax || (t == L.tmax && L.best.inst != 0xFFFFFFFFu &&
                                (inst < L.best.inst || (inst == L.best.inst && prim < L.best.prim)));
   if (!closer) return false;
   L.best.t = t, L.best.b1 = b1, L.best.b2 = b2, L.best.inst = inst, L.best.prim = prim;
   L.tmax = t;
-  L.found = true;
   return ANY;
 }
 
-// Persistent warp loop.  Policy: load(i, o, d, tmin, tmax) reads ray i; commit(i, found, hit) stores its result.
+#ifndef ASUNA_TICKET_CHUNK
+#define ASUNA_TICKET_CHUNK 64  // rays a warp takes from the queue per atomic (shrunk for short queues)
+#endif
+
+// Persistent warp loop.  Policy: tag = load(i, o, d, tmin, tmax) reads ray i; commit(i, tag, found, hit) stores its
+// result (tag = whatever the policy wants back, e.g. the path slot).
 template <bool ANY, bool COUNT, bool SINGLE, class Policy>
 __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t count, uint32_t* ticket, uint32_t* overflow,
                                  unsigned long long* node_visits, unsigned long long* tri_tests) {
   const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
   Lane L;
-  uint2 stack[kStackSize];
-  L.sp = 0, L.blas_sp = 0, L.in_blas = false, L.found = false, L.shear_ok = false;
-  L.ng = L.tg = make_uint2(0u, 0u);
+  uint2 stack[kStackSize + 1];
+  L.sp = 0, L.blas_sp = 0, L.in_blas = false, L.shear_ok = false;
+  L.ng = L.tg = L.top = make_uint2(0u, 0u);
   bool active = false, exhausted = (count == 0) || sc.n_instances == 0;
-  uint32_t ray = 0, n_nodes = 0, n_tris = 0;
+  uint32_t ray = 0, tag = 0, n_nodes = 0, n_tris = 0;
   if (sc.n_instances == 0) {  // nothing to hit: every ray misses
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x); i < count; i += gridDim.x * blockDim.x) {
       float3 o, d;
       float t0, t1;
-      pol.load(i, o, d, t0, t1);
+      const uint32_t g = pol.load(i, o, d, t0, t1);
       lane_begin<SINGLE>(L, sc, o, d, t0, t1);
-      pol.commit(i, false, L.best);
+      pol.commit(i, g, false, L.best);
     }
     return;
   }
+  // work fetch: the warp owns the index range [w_next, w_end) of the queue and takes a new chunk with one atomic
+  // when it runs dry; chunks shrink for short queues so that every warp of the grid still gets work
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t chunk = min((uint32_t)ASUNA_TICKET_CHUNK, max(count / (n_warps * 4u), 1u));
+  uint32_t w_next = 0, w_end = 0;
   for (;;) {
-    // ---- refill idle lanes from the queue: one atomic per warp
+    // ---- refill idle lanes from the queue
     const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
     if (!exhausted && idle) {
-      const uint32_t n_idle = __popc(idle), leader = (uint32_t)__ffs((int)idle) - 1u;
-      uint32_t base = 0;
-      if (lane == leader) base = atomicAdd(ticket, n_idle);
-      base = __shfl_sync(0xFFFFFFFFu, base, (int)leader);
-      if (!active) {
-        const uint32_t i = base + __popc(idle & lt);
-        if (i < count) {
-          float3 o, d;
-          float t0, t1;
-          pol.load(i, o, d, t0, t1);
-          lane_begin<SINGLE>(L, sc, o, d, t0, t1);
-          ray = i;
-          active = true;
-        }
+      const uint32_t n_idle = __popc(idle), avail = w_end - w_next;
+      uint32_t i = w_next + __popc(idle & lt);
+      if (avail < n_idle) {  // warp-uniform: finish the old chunk, continue in a fresh one
+        const uint32_t take = max(chunk, n_idle);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ticket, take);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (i >= w_end) i = base + (i - w_end);
+        w_next = base + (n_idle - avail), w_end = base + take;
+      } else {
+        w_next += n_idle;
       }
-      if (base + n_idle >= count) exhausted = true;
+      if (!active && i < count) {
+        float3 o, d;
+        float t0, t1;
+        tag = pol.load(i, o, d, t0, t1);
+        lane_begin<SINGLE>(L, sc, o, d, t0, t1);
+        ray = i;
+        active = true;
+      }
+      if (w_next >= count) exhausted = true;
     }
     if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
     // ---- traverse until enough lanes have finished to make a refill worthwhile
@@ -325,35 +348,35 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
             setup_space(L.rs, L.wo, L.wd);
           }
           if (L.sp == 0) {
-            pol.commit(ray, L.found, L.best);
+            pol.commit(ray, tag, L.best.inst != 0xFFFFFFFFu, L.best);
             active = false;
           } else {
-            const uint2 e = stack[--L.sp];
+            const uint2 e = lane_pop(L, stack);
             if (e.y > 0x00FFFFFFu) L.ng = e;
             else L.tg = e;
           }
-        } else if ((SINGLE || L.in_blas) && L.sp > (SINGLE ? 0 : L.blas_sp) && stack[L.sp - 1].y > 0x00FFFFFFu) {
-          const uint2 e = stack[L.sp - 1];
-          stack[L.sp - 1] = L.tg;
-          L.ng = e;
+        } else if ((SINGLE || L.in_blas) && L.sp > (SINGLE ? 0 : L.blas_sp) && L.top.y > 0x00FFFFFFu) {
+          L.ng = L.top;
+          L.top = L.tg;
           L.tg = make_uint2(0u, 0u);
         }
       }
+      const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, active);
+      if (m_act == 0u) break;
       if (active && L.ng.y > 0x00FFFFFFu) lane_node_step<COUNT, SINGLE>(L, stack, sc, overflow, n_nodes);
       if (!SINGLE && active && !L.in_blas && L.tg.y) lane_enter_instance(L, stack, sc, overflow);
       const bool want_tri = active && (SINGLE || L.in_blas) && L.tg.y != 0u;
       const uint32_t m_tri = __ballot_sync(0xFFFFFFFFu, want_tri);
-      const uint32_t m_node = __ballot_sync(0xFFFFFFFFu, active && L.ng.y > 0x00FFFFFFu);
-      const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, active);
-      if (m_tri && (m_node == 0u || __popc(m_tri) >= (__popc(m_act) >> sc.tri_vote_shift))) {
-        if (want_tri && lane_triangle_step<ANY, COUNT, SINGLE>(L, sc, n_tris)) {
-          pol.commit(ray, true, L.best);
-          active = false;
+      if (m_tri) {
+        const uint32_t m_node = __ballot_sync(0xFFFFFFFFu, active && L.ng.y > 0x00FFFFFFu);
+        if (m_node == 0u || __popc(m_tri) >= (__popc(m_act) >> sc.tri_vote_shift)) {
+          if (want_tri && lane_triangle_step<ANY, COUNT, SINGLE>(L, sc, n_tris)) {
+            pol.commit(ray, tag, true, L.best);
+            active = false;
+          }
         }
       }
-      const uint32_t still = __ballot_sync(0xFFFFFFFFu, active);
-      if (still == 0u) break;
-      if (!exhausted && 32u - __popc(still) >= sc.refill_lanes) break;
+      if (!exhausted && 32u - __popc(m_act) >= sc.refill_lanes) break;
     }
   }
   if (COUNT) {
