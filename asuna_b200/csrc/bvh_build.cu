@@ -242,7 +242,10 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const uint64_t* __res
 // ---- 4. PLOC: binary hierarchy by locally-ordered clustering + SAH collapse table ------------
 // Binary-node numbering during the build: leaf j (sorted position) is n-1+j; inner nodes are handed
 // out from n-2 downwards in merge order, so the last merge -- the root -- is node 0.
-constexpr int kPlocRadius = 10;
+#ifndef ASUNA_PLOC_RADIUS
+#define ASUNA_PLOC_RADIUS 10
+#endif
+constexpr int kPlocRadius = ASUNA_PLOC_RADIUS;
 constexpr uint64_t kDecLeaf = 1ull;
 
 struct PlocParams {

@@ -87,7 +87,7 @@ struct UserPolicy {  // asuna_trace_rays / asuna_occlusion_rays / asuna_trace_pr
 };
 
 template <bool COUNT, bool SINGLE>
-__global__ void __launch_bounds__(kTraceThreads, ASUNA_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTraceThreads, SINGLE ? ASUNA_TRACE_MIN_BLOCKS_SINGLE : ASUNA_TRACE_MIN_BLOCKS)
 k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter, int qsel) {
   ClosestPolicy pol{ps, ps.queue[qsel], sc.instances};
   trace_persistent<false, COUNT, SINGLE>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow,
@@ -95,7 +95,7 @@ k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cn
 }
 
 template <bool SINGLE>
-__global__ void __launch_bounds__(kTraceThreads, ASUNA_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTraceThreads, SINGLE ? ASUNA_TRACE_MIN_BLOCKS_SINGLE : ASUNA_TRACE_MIN_BLOCKS)
 k_trace_shadow(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter) {
   ShadowPolicy pol{ps};
   trace_persistent<true, false, SINGLE>(sc, pol, cnt->shadow[iter], &cnt->ticket_shadow[iter], &cnt->stack_overflow, nullptr,
@@ -439,10 +439,10 @@ void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView&
                           int iter, int qsel, bool counting) {
   const bool single = sc.single_root != 0xFFFFFFFFu;  // every instance merged into the world BLAS: no instance level
   if (counting) {
-    if (single) k_trace_closest<true, true><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+    if (single) k_trace_closest<true, true><<<ld.trace_blocks_single, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
     else k_trace_closest<true, false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
   } else {
-    if (single) k_trace_closest<false, true><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
+    if (single) k_trace_closest<false, true><<<ld.trace_blocks_single, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
     else k_trace_closest<false, false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
   }
 }
@@ -485,7 +485,7 @@ int launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, cons
 }
 void launch_trace_shadow(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
                          int iter) {
-  if (sc.single_root != 0xFFFFFFFFu) k_trace_shadow<true><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
+  if (sc.single_root != 0xFFFFFFFFu) k_trace_shadow<true><<<ld.trace_blocks_single, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
   else k_trace_shadow<false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
 }
 void launch_accumulate(cudaStream_t s, const FrameParams& fp, const PathState& ps, const OutputImages& out) {
@@ -535,6 +535,9 @@ cudaError_t query_launch_dims(LaunchDims& ld, int sm_count) {
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest<false, false>, kTraceThreads, 0);
   if (e != cudaSuccess) return e;
   ld.trace_blocks = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest<false, true>, kTraceThreads, 0);
+  if (e != cudaSuccess) return e;
+  ld.trace_blocks_single = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
   return shade_occupancy(ld, sm_count, std::make_integer_sequence<uint32_t, kNumKinds>{});
 }
 

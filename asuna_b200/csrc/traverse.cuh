@@ -15,6 +15,8 @@
 // traversing ("triangle postponing", Ylitie et al. 2017 section 5).  Finished lanes are refilled from the
 // ray queue with one atomic per warp as soon as `refill_lanes` of them are idle.
 #pragma once
+#include <cuda_fp16.h>
+
 #include "device_types.cuh"
 #include "vec.cuh"
 
@@ -22,7 +24,10 @@ namespace asuna {
 
 constexpr int kTraceThreads = 128;
 #ifndef ASUNA_TRACE_MIN_BLOCKS
-#define ASUNA_TRACE_MIN_BLOCKS 6  // 80 registers: 24 resident warps per SM (measured best; 8 blocks spills)
+#define ASUNA_TRACE_MIN_BLOCKS 6  // two-level kernels, 80 registers: 24 resident warps per SM (measured best; 7 spills)
+#endif
+#ifndef ASUNA_TRACE_MIN_BLOCKS_SINGLE
+#define ASUNA_TRACE_MIN_BLOCKS_SINGLE 7  // single-level kernels fit 72 registers without spilling: 28 warps per SM (+5 %)
 #endif
 constexpr int kStackSize = 40;        // uint2 entries: wide-BVH depth of the instance level + one mesh level
 
@@ -118,18 +123,41 @@ ADEV float magic_byte(uint32_t v, uint32_t magic) {
 template <int J>
 ADEV uint32_t byte_of(uint32_t x) { return __byte_perm(x, 0u, 0x4440 + J); }
 
+// Two quantised planes per PRMT: bytes (2K, 2K+1) of v become the half2 (1024 + q, 1024 + q') -- exact in fp16 --
+// and two HADD2.F32 on the FMA pipe widen them.  Trades one ALU-pipe PRMT for two FMA-pipe conversions per pair;
+// ASUNA_HALF_UNPACK selects which planes go this way (0 none, 1 the far planes, 2 all).
+#ifndef ASUNA_HALF_UNPACK
+#define ASUNA_HALF_UNPACK 0
+#endif
+template <int K>
+ADEV float2 half_pair(uint32_t v, uint32_t magic_h) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(v), "r"(magic_h), "n"(K == 0 ? 0x4140 : 0x4342));
+  return __half22float2(*reinterpret_cast<__half2*>(&d));
+}
+template <bool HALF>
+ADEV void unpack4(uint32_t v, uint32_t magic, float f[4]) {
+  if (HALF) {
+    const float2 a = half_pair<0>(v, 0x64646464u), b = half_pair<1>(v, 0x64646464u);
+    f[0] = a.x, f[1] = a.y, f[2] = b.x, f[3] = b.y;
+  } else {
+    f[0] = magic_byte<0>(v, magic), f[1] = magic_byte<1>(v, magic), f[2] = magic_byte<2>(v, magic), f[3] = magic_byte<3>(v, magic);
+  }
+}
+
 ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 n4, const RaySpace& r, float tmin,
                                   float tmax, uint32_t magic) {
-  const float kBias = 8388608.0f, kWiden = 1.0000004f;
+  constexpr bool kHalfNear = ASUNA_HALF_UNPACK >= 2, kHalfFar = ASUNA_HALF_UNPACK >= 1;
+  const float kWiden = 1.0000004f;
   const float ax = __uint_as_float((n0.w & 0xFFu) << 23) * r.idir.x;
   const float ay = __uint_as_float(((n0.w >> 8) & 0xFFu) << 23) * r.idir.y;
   const float az = __uint_as_float(((n0.w >> 16) & 0xFFu) << 23) * r.idir.z;
-  const float bx = fmaf(-kBias, ax, (__uint_as_float(n0.x) - r.o.x) * r.idir.x);
-  const float by = fmaf(-kBias, ay, (__uint_as_float(n0.y) - r.o.y) * r.idir.y);
-  const float bz = fmaf(-kBias, az, (__uint_as_float(n0.z) - r.o.z) * r.idir.z);
+  const float cx = (__uint_as_float(n0.x) - r.o.x) * r.idir.x, cy = (__uint_as_float(n0.y) - r.o.y) * r.idir.y,
+              cz = (__uint_as_float(n0.z) - r.o.z) * r.idir.z;
   const float hx = 0.50001f * fabsf(ax), hy = 0.50001f * fabsf(ay), hz = 0.50001f * fabsf(az);
-  const float bnx = bx - hx, bny = by - hy, bnz = bz - hz;
-  const float bfx = bx + hx, bfy = by + hy, bfz = bz + hz;
+  const float kBn = kHalfNear ? 1024.0f : 8388608.0f, kBf = kHalfFar ? 1024.0f : 8388608.0f;
+  const float bnx = fmaf(-kBn, ax, cx) - hx, bny = fmaf(-kBn, ay, cy) - hy, bnz = fmaf(-kBn, az, cz) - hz;
+  const float bfx = fmaf(-kBf, ax, cx) + hx, bfy = fmaf(-kBf, ay, cy) + hy, bfz = fmaf(-kBf, az, cz) + hz;
   const bool nx = (r.oct & 1u) != 0u, ny = (r.oct & 2u) != 0u, nz = (r.oct & 4u) != 0u;
   const uint32_t octinv4 = (7u ^ r.oct) * 0x01010101u;
   uint32_t mask = 0;
@@ -143,14 +171,15 @@ ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 
     const uint32_t child_bits4 = (meta4 >> 5) & 0x07070707u;
     const uint32_t qlx = h ? n2.y : n2.x, qly = h ? n2.w : n2.z, qlz = h ? n3.y : n3.x;
     const uint32_t qhx = h ? n3.w : n3.z, qhy = h ? n4.y : n4.x, qhz = h ? n4.w : n4.z;
-    const uint32_t nearx = nx ? qhx : qlx, farx = nx ? qlx : qhx;
-    const uint32_t neary = ny ? qhy : qly, fary = ny ? qly : qhy;
-    const uint32_t nearz = nz ? qhz : qlz, farz = nz ? qlz : qhz;
+    float qnx[4], qny[4], qnz[4], qfx[4], qfy[4], qfz[4];
+    unpack4<kHalfNear>(nx ? qhx : qlx, magic, qnx), unpack4<kHalfFar>(nx ? qlx : qhx, magic, qfx);
+    unpack4<kHalfNear>(ny ? qhy : qly, magic, qny), unpack4<kHalfFar>(ny ? qly : qhy, magic, qfy);
+    unpack4<kHalfNear>(nz ? qhz : qlz, magic, qnz), unpack4<kHalfFar>(nz ? qlz : qhz, magic, qfz);
 #define ASUNA_CHILD(J)                                                                                      \
     {                                                                                                         \
-      float tnx = fmaf(magic_byte<J>(nearx, magic), ax, bnx), tfx = fmaf(magic_byte<J>(farx, magic), ax, bfx); \
-      float tny = fmaf(magic_byte<J>(neary, magic), ay, bny), tfy = fmaf(magic_byte<J>(fary, magic), ay, bfy); \
-      float tnz = fmaf(magic_byte<J>(nearz, magic), az, bnz), tfz = fmaf(magic_byte<J>(farz, magic), az, bfz); \
+      float tnx = fmaf(qnx[J], ax, bnx), tfx = fmaf(qfx[J], ax, bfx);                                         \
+      float tny = fmaf(qny[J], ay, bny), tfy = fmaf(qfy[J], ay, bfy);                                         \
+      float tnz = fmaf(qnz[J], az, bnz), tfz = fmaf(qfz[J], az, bfz);                                         \
       float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                  \
       float cmax = fminf(fminf(fminf(tfx, tfy), tfz) * kWiden, tmax);                                         \
       if (cmin <= cmax) mask |= byte_of<J>(child_bits4) << byte_of<J>(bit_index4);                            \
