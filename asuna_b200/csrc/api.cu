@@ -74,6 +74,8 @@ struct asuna_ctx {
   // frame state
   AsunaCamera cam{};
   AsunaSunSky sunsky{};
+  float sky_ground_irrad[3] = {0.f, 0.f, 0.f};  // of `sunsky`, evaluated on the device when it changes
+  bool sky_irrad_valid = false;
   AsunaState pc{};
   uint32_t rank = 0, world = 1;
   bool have_accum = false;
@@ -245,6 +247,7 @@ FrameParams make_frame_params(asuna_ctx* ctx) {
   FrameParams fp{};
   fp.cam = ctx->cam;
   fp.sunsky = ctx->sunsky;
+  for (int k = 0; k < 3; k++) fp.sky_ground_irrad[k] = ctx->sky_ground_irrad[k];
   fp.pc = ctx->pc;
   fp.width = ctx->W;
   fp.height = ctx->H;
@@ -293,7 +296,7 @@ int asuna_create(asuna_ctx** out, int gpu_id) {
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&ctx->d_counters, sizeof(Counters)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_totals, sizeof(Totals)) != cudaSuccess ||
+      cudaMalloc(&ctx->d_totals, 2 * sizeof(Totals))  /* [1] = scratch for small device->host results */ != cudaSuccess ||
       cudaMemset(ctx->d_totals, 0, sizeof(Totals)) != cudaSuccess ||
       cudaMallocHost(&ctx->h_totals, sizeof(Totals)) != cudaSuccess ||
       query_launch_dims(ctx->dims, ctx->sm_count) != cudaSuccess) {
@@ -649,7 +652,16 @@ int asuna_set_camera(asuna_ctx* ctx, const AsunaCamera* c) {
 }
 int asuna_set_sunsky(asuna_ctx* ctx, const AsunaSunSky* s) {
   if (!s) return fail(ctx, ASUNA_E_INVALID, "null sunsky");
+  const bool changed = memcmp(&ctx->sunsky, s, sizeof *s) != 0;
   ctx->sunsky = *s;
+  if (s->in_use == 1 && (changed || !ctx->sky_irrad_valid)) {
+    // the model's ground irradiance depends on the sun setting only: one device evaluation per setting, not per lookup
+    cudaSetDevice(ctx->device);
+    launch_sky_ground_irradiance(ctx->stream, ctx->sunsky, reinterpret_cast<float*>(ctx->d_totals + 1));
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->sky_ground_irrad, ctx->d_totals + 1, 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->sky_irrad_valid = true;
+  }
   return 0;
 }
 int asuna_set_state(asuna_ctx* ctx, const AsunaState* st) {
@@ -850,7 +862,18 @@ int asuna_trace_rays(asuna_ctx* ctx, const float* rays, uint32_t n, float* tuv, 
   int rc = upload_user_rays(ctx, rays, n);
   if (rc) return rc;
   ASUNA_CUDA_CHECK(cudaMemsetAsync(&ctx->d_counters->stack_overflow, 0, sizeof(uint32_t), ctx->stream));
+  const bool timed = getenv("ASUNA_TIME_USER_RAYS") != nullptr;  // developer probe (tools/coherence_probe.py): kernel ms on stderr
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (timed) cudaEventCreate(&e0), cudaEventCreate(&e1), cudaEventRecord(e0, ctx->stream);
   launch_trace_user(ctx->stream, ctx->dims, ctx->view, ctx->d_user_rays, n, ctx->d_user_tuv, ctx->d_user_ip, nullptr, ctx->d_counters);
+  if (timed) {
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "asuna_trace_rays: %u rays in %.4f ms = %.1f Mrays/s\n", n, ms, n / ms / 1e3);
+    cudaEventDestroy(e0), cudaEventDestroy(e1);
+  }
   if (tuv) ASUNA_CUDA_CHECK(cudaMemcpyAsync(tuv, ctx->d_user_tuv, (size_t)n * 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(ip, ctx->d_user_ip, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));

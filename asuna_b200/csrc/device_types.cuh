@@ -141,6 +141,7 @@ struct FrameParams {
   uint32_t n_frames;                 // frames in this batch
   int32_t frame_ids[64];             // curFrame value of each batch frame
   uint32_t first_is_replace;         // first frame of the batch replaces the accumulation buffer
+  float sky_ground_irrad[3];         // sun & sky: calc_irrad of the current sun setting (shading.cuh sky_ground_irradiance)
 };
 #define ASUNA_MAX_BATCH_FRAMES 64
 

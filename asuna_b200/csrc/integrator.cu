@@ -108,6 +108,12 @@ k_trace_user(const __grid_constant__ SceneView sc, UserPolicy pol, uint32_t n, u
   trace_persistent<ANY, false, SINGLE>(sc, pol, n, ticket, &cnt->stack_overflow, nullptr, nullptr);
 }
 
+// Sun & sky: the ground irradiance of the current sun setting, once per setting instead of once per lookup.
+__global__ void k_sky_ground_irradiance(AsunaSunSky ss, float* out) {
+  const float3 v = sky_ground_irradiance(ss);
+  out[0] = v.x, out[1] = v.y, out[2] = v.z;
+}
+
 // Adds one batch's per-iteration counters into the persistent totals (one thread; a few hundred words).
 __global__ void k_fold_counters(const Counters* cnt, Totals* tot, int iters) {
   unsigned long long c = 0, s = 0, inc = 0;
@@ -445,6 +451,9 @@ void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView&
     if (single) k_trace_closest<false, true><<<ld.trace_blocks_single, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
     else k_trace_closest<false, false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
   }
+}
+void launch_sky_ground_irradiance(cudaStream_t s, const AsunaSunSky& ss, float* out3) {
+  k_sky_ground_irradiance<<<1, 1, 0, s>>>(ss, out3);
 }
 void launch_fold_counters(cudaStream_t s, const Counters* cnt, Totals* tot, int iters) {
   k_fold_counters<<<1, 1, 0, s>>>(cnt, tot, iters);

@@ -221,8 +221,40 @@ ADEV float3 tweak_vector(float3 d, int y_is_up, float horiz_height) {  // :278-2
   }
   return o;
 }
+// Sun vector as the model uses it (:436-447): tweaked, lifted to z >= 0.001; `factor` = night brightness adjustment.
+ADEV float3 sun_vector(const AsunaSunSky& ss, float horiz, float& factor, float3& real_sun) {
+  float3 sun = tweak_vector(normalize(f3(ss.sun_direction)), ss.y_is_up, horiz);
+  real_sun = sun;
+  if (sun.z < 0.001f) {
+    if (sun.z < 0.0f) {  // night_brightness_adjustment :396-403
+      const float lmt = 0.30901699437494742410229341718282f;
+      if (sun.z <= -lmt) factor = 0.0f;
+      else {
+        float f = (sun.z + lmt) / lmt;
+        f *= f;
+        factor = f * f;
+      }
+    }
+    sun.z = 0.001f;
+    sun = normalize(sun);
+  }
+  return sun;
+}
+// calc_irrad :245-262 (float loop counters as written): mean sky colour over a 5x5 cosine stencil around +z.  It
+// depends on the sun parameters only, not on the ray, so it is evaluated once per sun/sky setting
+// (k_sky_ground_irradiance, integrator.cu) and handed to every below-horizon lookup through FrameParams.
+ADEV float3 sky_ground_irradiance(const AsunaSunSky& ss) {
+  float factor = 1.0f;
+  float3 real_sun;
+  float3 sun = sun_vector(ss, ss.horizon_height / 10.0f, factor, real_sun);
+  float3 irrad = f3(0.0f);
+  for (float u = 1.f / 10.f; u < 1.f; u += 1.f / 5.f)
+    for (float v = 1.f / 10.f; v < 1.f; v += 1.f / 5.f) irrad += sky_env_color(sun, ground_stencil_dir(u, v), 2.0f);
+  irrad /= 25.0f;
+  return irrad;
+}
 // :405-533
-__device__ __noinline__ float3 sun_and_sky(const AsunaSunSky& ss, float3 in_dir) {
+__device__ __noinline__ float3 sun_and_sky(const AsunaSunSky& ss, float3 in_dir, float3 ground_irrad) {
   float factor = 1.0f, night_factor = 1.0f;
   float3 rgb_scale = f3(ss.rgb_unit_conversion);
   float horiz = ss.horizon_height / 10.0f;
@@ -247,21 +279,8 @@ __device__ __noinline__ float3 sun_and_sky(const AsunaSunSky& ss, float3 in_dir)
     dir.z = 0.001f;
     dir = normalize(dir);
   }
-  float3 sun = tweak_vector(normalize(f3(ss.sun_direction)), ss.y_is_up, horiz);
-  float3 real_sun = sun;
-  if (sun.z < 0.001f) {
-    if (sun.z < 0.0f) {  // night_brightness_adjustment :396-403
-      const float lmt = 0.30901699437494742410229341718282f;
-      if (sun.z <= -lmt) factor = 0.0f;
-      else {
-        float f = (sun.z + lmt) / lmt;
-        f *= f;
-        factor = f * f;
-      }
-    }
-    sun.z = 0.001f;
-    sun = normalize(sun);
-  }
+  float3 real_sun;
+  float3 sun = sun_vector(ss, horiz, factor, real_sun);
   float3 tint = f3(0.0f);
   if (factor > 0.0f) {
     tint = sky_env_color(sun, dir, haze);
@@ -297,10 +316,7 @@ __device__ __noinline__ float3 sun_and_sky(const AsunaSunSky& ss, float3 in_dir)
   }
   float3 out = tint * rgb_scale;
   if (downness <= 0.0f) {
-    float3 irrad = f3(0.0f);  // calc_irrad :245-262, float loop counters as written
-    for (float u = 1.f / 10.f; u < 1.f; u += 1.f / 5.f)
-      for (float v = 1.f / 10.f; v < 1.f; v += 1.f / 5.f) irrad += sky_env_color(sun, ground_stencil_dir(u, v), 2.0f);
-    irrad /= 25.0f;
+    const float3 irrad = ground_irrad;  // calc_irrad :245-262, hoisted: see sky_ground_irradiance
     float3 down = f3(ss.ground_color) * ((irrad + sun_color * sun.z) * rgb_scale);
     if (factor < 1) down *= factor;
     float blur = ss.horizon_blur / 10.0f;
@@ -454,7 +470,7 @@ ADEV float3 sample_lights(const ShadeEnv& se, PathRegs& p, float3 pos, float3 no
     if (sk.in_use == 1) {
       ls.d = uniform_sample_sphere(u);
       ls.pdf = kInv4Pi;
-      radiance = sun_and_sky(sk, ls.d);
+      radiance = sun_and_sky(sk, ls.d, f3(se.fp->sky_ground_irrad));
     } else if (pc.hasEnvMap == 1) {
       radiance = env_sample(se.env, u, ls.d, ls.pdf);
     } else {
@@ -1348,7 +1364,7 @@ ADEV void shade_miss(const ShadeEnv& se, PathRegs& p) {
   const AsunaSunSky& sk = se.fp->sunsky;
   p.stop = true;
   float3 d = p.ray_d, env;
-  if (sk.in_use == 1) env = sun_and_sky(sk, d);
+  if (sk.in_use == 1) env = sun_and_sky(sk, d, f3(se.fp->sky_ground_irrad));
   else if (pc.hasEnvMap == 1) env = env_eval(se.env, d);
   else env = f3(pc.bgColor);
   float mis = 1.0f;

@@ -1,6 +1,6 @@
 """C4' ray-throughput check: ~1.3 M-triangle mesh, lambertian, white environment, 1080p.
 Incoherent rays = closest-hit rays at depth >= 2 (after a cosine-hemisphere bounce).
-usage: python tools/ray_bench.py [subdiv=8] [frames=16] [scene=rays|glass|field]"""
+usage: python tools/ray_bench.py [subdiv=8] [frames=16] [scene=rays|glass|field|pbr]"""
 import json
 import os
 import sys
@@ -21,6 +21,8 @@ elif which == "rays_merged":  # same geometry as one mesh / one instance: what a
     sc.meshes = [(np.concatenate([v0, v1]), np.concatenate([i0, i1 + len(v0)]))]
     sc.mesh_ids = {"blob": 0}
     sc.instances = sc.instances[:1]
+elif which == "pbr":  # C3: textured PBR spheres, sun/sky + point light
+    sc = scenes.pbr_spheres(1920, 1080, depth=5, subdiv=subdiv)
 elif which == "glass":
     sc = scenes.glass_blob(1920, 1080, subdiv=subdiv, env_size=(2048, 1024))
 else:
