@@ -260,8 +260,22 @@ __global__ void __launch_bounds__(256) k_bin_scatter(PathState ps, const Counter
 }
 
 // ---- shading: one kernel per hit kind (≙ one closest-hit / miss shader each) -----------------------
+// Resident blocks per SM the shade kernels are compiled for.  They are latency-bound (dependent gathers: instance ->
+// indices -> vertices -> material -> texels), so occupancy beats register-resident state: 8 blocks (64 registers, the
+// rest in L1-resident local memory) is neutral for the texture-free shaders and +14 % on the textured PBR config; the
+// shaders that fetch up to five textures per hit (pbr, kang18, disney) keep gaining up to 12 blocks (+19 %).
+#ifndef ASUNA_SHADE_MIN_BLOCKS
+#define ASUNA_SHADE_MIN_BLOCKS 8
+#endif
+#ifndef ASUNA_SHADE_MIN_BLOCKS_TEXTURED
+#define ASUNA_SHADE_MIN_BLOCKS_TEXTURED 12
+#endif
+constexpr bool shade_kind_textured(uint32_t kind) {
+  return kind == kKindMaterial0 + ASUNA_MAT_PBR_METALNESS_ROUGHNESS || kind == kKindMaterial0 + ASUNA_MAT_KANG18 ||
+         kind == kKindMaterial0 + ASUNA_MAT_DISNEY;
+}
 template <uint32_t KIND>
-__global__ void __launch_bounds__(kShadeThreads)
+__global__ void __launch_bounds__(kShadeThreads, shade_kind_textured(KIND) ? ASUNA_SHADE_MIN_BLOCKS_TEXTURED : ASUNA_SHADE_MIN_BLOCKS)
 k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParams fp, PathState ps, OutputImages out, Counters* cnt, int iter,
         int qsel, uint32_t n_blocks) {
   const uint32_t begin = ps.bin_hist[KIND * n_blocks];

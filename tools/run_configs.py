@@ -36,14 +36,15 @@ for name, build in CONFIGS:
     build_ms = sc.upload(ctx)
     acc = ctx.accel_stats()
     shots = range(len(sc.shots)) if name.startswith("C5") else [0]
+    per_shot = frames if len(shots) == 1 else max(frames // 4, 2)
     sc.begin_shot(ctx, 0)
-    ctx.render_frames(4)  # warm-up
+    ctx.render_frames(per_shot)  # warm-up with the timed batch shape (path buffers are sized on first use)
     ctx.sync()
     ctx.reset_stats()
     t0 = time.perf_counter()
     for s in shots:
         sc.begin_shot(ctx, s)
-        ctx.render_frames(frames if len(shots) == 1 else max(frames // 4, 2))
+        ctx.render_frames(per_shot)
     ctx.sync()
     wall = time.perf_counter() - t0
     st = ctx.stats()
