@@ -918,6 +918,12 @@ int asuna_accel_stats(asuna_ctx* ctx, uint64_t out[4]) {
 
 // Test hook (not part of the reference-facing surface): sorts n (key, value) pairs given as host
 // arrays with the builder's radix sort, so the sort can be checked bit-exactly on its own.
+// Developer probe: warp-loop occupancy counters of the instrumented traversal (see Counters::lane_stats); valid after
+// asuna_get_stats has fetched the totals.
+int asuna_debug_lane_stats(asuna_ctx* ctx, uint64_t out[6]) {
+  for (int k = 0; k < 6; k++) out[k] = ctx->h_totals->lane_stats[k];
+  return 0;
+}
 int asuna_debug_radix_sort(asuna_ctx* ctx, uint64_t* keys, uint32_t* vals, uint32_t n) {
   if (n == 0) return 0;
   cudaSetDevice(ctx->device);

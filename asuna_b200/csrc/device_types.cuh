@@ -124,12 +124,16 @@ struct Counters {
   uint32_t stack_overflow;
   unsigned long long node_visits;   // instrumented traversal only (asuna_set_counting)
   unsigned long long tri_tests;
+  // warp-loop occupancy of the instrumented traversal: iterations, sum of live lanes, lanes in node steps, lanes
+  // wanting a triangle step, triangle steps run, lanes in them
+  unsigned long long lane_stats[6];
 };
 
 // Totals folded from `Counters` at the end of every batch by k_fold_counters (no host sync needed).
 struct Totals {
   unsigned long long closest_rays, shadow_rays, incoherent_rays, node_visits, tri_tests;
   unsigned long long stack_overflow;
+  unsigned long long lane_stats[6];
 };
 
 struct FrameParams {

@@ -91,7 +91,7 @@ __global__ void __launch_bounds__(kTraceThreads, SINGLE ? ASUNA_TRACE_MIN_BLOCKS
 k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter, int qsel) {
   ClosestPolicy pol{ps, ps.queue[qsel], sc.instances};
   trace_persistent<false, COUNT, SINGLE>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow,
-                                 &cnt->node_visits, &cnt->tri_tests);
+                                         &cnt->node_visits, &cnt->tri_tests, cnt->lane_stats);
 }
 
 template <bool SINGLE>
@@ -124,6 +124,7 @@ __global__ void k_fold_counters(const Counters* cnt, Totals* tot, int iters) {
   tot->node_visits += cnt->node_visits;
   tot->tri_tests += cnt->tri_tests;
   tot->stack_overflow += cnt->stack_overflow;
+  for (int k = 0; k < 6; k++) tot->lane_stats[k] += cnt->lane_stats[k];
 }
 
 // ---- camera: raytrace.projective.rgen:41-87 ---------------------------------------------------

@@ -316,7 +316,8 @@ ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
 // result (tag = whatever the policy wants back, e.g. the path slot).
 template <bool ANY, bool COUNT, bool SINGLE, class Policy>
 __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t count, uint32_t* ticket, uint32_t* overflow,
-                                 unsigned long long* node_visits, unsigned long long* tri_tests) {
+                                 unsigned long long* node_visits, unsigned long long* tri_tests,
+                                 unsigned long long* lane_stats = nullptr) {
   const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
   Lane L;
   uint2 stack[kStackSize + 1];
@@ -324,6 +325,7 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
   L.ng = L.tg = L.top = make_uint2(0u, 0u);
   bool active = false, exhausted = (count == 0) || sc.n_instances == 0;
   uint32_t ray = 0, tag = 0, n_nodes = 0, n_tris = 0;
+  uint32_t ls_iter = 0, ls_act = 0, ls_node = 0, ls_want = 0, ls_fired = 0, ls_tri = 0;  // COUNT only (warp-uniform)
   if (sc.n_instances == 0) {  // nothing to hit: every ray misses
     for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x); i < count; i += gridDim.x * blockDim.x) {
       float3 o, d;
@@ -392,13 +394,16 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
       }
       const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, active);
       if (m_act == 0u) break;
+      if (COUNT) ls_iter++, ls_act += __popc(m_act), ls_node += __popc(__ballot_sync(0xFFFFFFFFu, active && L.ng.y > 0x00FFFFFFu));
       if (active && L.ng.y > 0x00FFFFFFu) lane_node_step<COUNT, SINGLE>(L, stack, sc, overflow, n_nodes);
       if (!SINGLE && active && !L.in_blas && L.tg.y) lane_enter_instance(L, stack, sc, overflow);
       const bool want_tri = active && (SINGLE || L.in_blas) && L.tg.y != 0u;
       const uint32_t m_tri = __ballot_sync(0xFFFFFFFFu, want_tri);
+      if (COUNT) ls_want += __popc(m_tri);
       if (m_tri) {
         const uint32_t m_node = __ballot_sync(0xFFFFFFFFu, active && L.ng.y > 0x00FFFFFFu);
         if (m_node == 0u || __popc(m_tri) >= (__popc(m_act) >> sc.tri_vote_shift)) {
+          if (COUNT) ls_fired++, ls_tri += __popc(m_tri);
           if (want_tri && lane_triangle_step<ANY, COUNT, SINGLE>(L, sc, n_tris)) {
             pol.commit(ray, tag, true, L.best);
             active = false;
@@ -416,6 +421,11 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
     if (lane == 0) {
       atomicAdd(node_visits, (unsigned long long)n_nodes);
       atomicAdd(tri_tests, (unsigned long long)n_tris);
+      if (lane_stats) {
+        atomicAdd(lane_stats + 0, (unsigned long long)ls_iter), atomicAdd(lane_stats + 1, (unsigned long long)ls_act);
+        atomicAdd(lane_stats + 2, (unsigned long long)ls_node), atomicAdd(lane_stats + 3, (unsigned long long)ls_want);
+        atomicAdd(lane_stats + 4, (unsigned long long)ls_fired), atomicAdd(lane_stats + 5, (unsigned long long)ls_tri);
+      }
     }
   }
 }

@@ -35,6 +35,15 @@ ctx.set_counting(True)
 ctx.render_frames(1)
 s = ctx.stats()
 npr, tpr = s["node_visits"] / s["closest_rays"], s["tri_tests"] / s["closest_rays"]
+import ctypes as _C
+_ls = (_C.c_uint64 * 6)()
+lane = None
+if hasattr(ctx.L.lib, "asuna_debug_lane_stats"):
+    ctx.L.lib.asuna_debug_lane_stats(ctx.h, _ls)
+    it, act, node, want, fired, tri = [float(x) for x in _ls]
+    if it:
+        lane = {"iters_per_32_rays": it / (s["closest_rays"] / 32), "live_lanes": act / it, "node_step_lanes": node / it,
+                "tri_wanting_lanes": want / it, "tri_steps_per_iter": fired / it, "tri_step_lanes": tri / max(fired, 1)}
 ctx.set_counting(False)
 sc.begin_shot(ctx, 0)
 ctx.render_frames(8)
@@ -45,7 +54,7 @@ ctx.sync()
 s = ctx.stats()
 print(json.dumps({
     "scene": which, "triangles": acc["leaf_prims"], "wide_nodes": acc["nodes"], "sah": acc["sah_cost"], "build_ms": build_ms,
-    "nodes_per_ray": npr, "tris_per_ray": tpr,
+    "nodes_per_ray": npr, "tris_per_ray": tpr, "lane_stats": lane,
     "incoherent_closest_Mrays_s": s["incoherent_closest_rays"] / s["closest_ms"] / 1e3 * (s["closest_rays"] / max(s["closest_rays"], 1)),
     "closest_Mrays_s": s["closest_rays"] / s["closest_ms"] / 1e3,
     "all_Mrays_s": (s["closest_rays"] + s["shadow_rays"]) / s["trace_ms"] / 1e3,
