@@ -56,5 +56,5 @@ for name, build in CONFIGS:
         "all_Mrays_s": round((st["closest_rays"] + st["shadow_rays"]) / max(st["trace_ms"], 1e-9) / 1e3),
         "incoherent_closest_Mrays_s": round(st["incoherent_closest_rays"] / max(st["closest_ms"], 1e-9) / 1e3),
         "ms": {k: round(st[k], 1) for k in ("closest_ms", "shadow_ms", "shade_ms", "total_ms")},
-        "scene_gen_s": round(gen_s, 1)}), flush=True)
+        "stack_overflow": st.get("stack_overflow", 0), "scene_gen_s": round(gen_s, 1)}), flush=True)
     ctx.close()
