@@ -627,6 +627,8 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   free_dev(d_soup);
   ctx->view.magic = 0x4B000000u;
   ctx->view.refill_lanes = 8, ctx->view.tri_vote_shift = 2;
+  ctx->view.stage_lanes = 16;
+  if (const char* t = getenv("ASUNA_STAGE_LANES")) ctx->view.stage_lanes = std::min(std::max(atoi(t), 1), 32);
   if (const char* t = getenv("ASUNA_TUNE")) {  // "refill,shift[,cost_prim x10]" -- traversal tuning experiments
     unsigned a = 8, b = 2, c = 0;
     if (sscanf(t, "%u,%u,%u", &a, &b, &c) >= 1) ctx->view.refill_lanes = std::min(std::max(a, 1u), 32u), ctx->view.tri_vote_shift = std::min(b, 5u);

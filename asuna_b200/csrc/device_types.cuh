@@ -90,6 +90,7 @@ struct SceneView {
   uint32_t magic;                 // 0x4B000000 from the constant bank: keeps the PRMT selectors immediate (traverse.cuh)
   uint32_t refill_lanes;          // traversal tuning (ASUNA_TUNE): refill when this many lanes are idle
   uint32_t tri_vote_shift;        // triangle step quorum = live lanes >> shift
+  uint32_t stage_lanes;           // prepared-ray slots are refilled once this many are empty (single-level kernels)
 };
 
 // ---- wavefront path state (structure of float4 arrays, one slot per in-flight path) -------

@@ -314,11 +314,20 @@ ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
 
 // Persistent warp loop.  Policy: tag = load(i, o, d, tmin, tmax) reads ray i; commit(i, tag, found, hit) stores its
 // result (tag = whatever the policy wants back, e.g. the path slot).
-template <bool ANY, bool COUNT, bool SINGLE, class Policy>
+//
+// STAGE (single-level kernels): every lane also keeps one PREPARED ray (origin, 1/direction, shear rows, interval, ids:
+// kStageWords words) in shared memory.  A lane whose ray finishes starts its prepared ray in the same iteration -- no
+// lane waits for a refill quorum -- and the prepared slots are refilled sc.stage_lanes at a time, so the queue fetch,
+// the global ray loads and the reciprocal / shear set-up run at least that wide.
+constexpr int kStageWords = 19;
+template <bool ANY, bool COUNT, bool SINGLE, bool STAGE, class Policy>
 __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t count, uint32_t* ticket, uint32_t* overflow,
                                  unsigned long long* node_visits, unsigned long long* tri_tests,
-                                 unsigned long long* lane_stats = nullptr) {
+                                 unsigned long long* lane_stats = nullptr, uint32_t* stage_words = nullptr) {
+  static_assert(!STAGE || SINGLE, "prepared rays are implemented for the single-level kernels");
   const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
+  uint32_t* const stg = STAGE ? stage_words + (threadIdx.x >> 5) * (kStageWords * 32) + lane : nullptr;
+  bool staged = false;
   Lane L;
   uint2 stack[kStackSize + 1];
   L.sp = 0, L.blas_sp = 0, L.in_blas = false, L.shear_ok = false;
@@ -341,9 +350,27 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
   const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
   const uint32_t chunk = min((uint32_t)ASUNA_TICKET_CHUNK, max(count / (n_warps * 4u), 1u));
   uint32_t w_next = 0, w_end = 0;
+  // start the prepared ray of this lane (STAGE)
+  auto take_staged = [&]() {
+    L.rs.o = f3(__uint_as_float(stg[0 * 32]), __uint_as_float(stg[1 * 32]), __uint_as_float(stg[2 * 32]));
+    L.rs.idir = f3(__uint_as_float(stg[3 * 32]), __uint_as_float(stg[4 * 32]), __uint_as_float(stg[5 * 32]));
+    L.rs.sx = f3(__uint_as_float(stg[6 * 32]), __uint_as_float(stg[7 * 32]), __uint_as_float(stg[8 * 32]));
+    L.rs.sy = f3(__uint_as_float(stg[9 * 32]), __uint_as_float(stg[10 * 32]), __uint_as_float(stg[11 * 32]));
+    L.rs.sz = f3(__uint_as_float(stg[12 * 32]), __uint_as_float(stg[13 * 32]), __uint_as_float(stg[14 * 32]));
+    L.rs.oct = (__float_as_uint(L.rs.idir.x) >> 31) | ((__float_as_uint(L.rs.idir.y) >> 31) << 1) |
+               ((__float_as_uint(L.rs.idir.z) >> 31) << 2);
+    L.tmin = __uint_as_float(stg[15 * 32]), L.tmax = __uint_as_float(stg[16 * 32]);
+    ray = stg[17 * 32], tag = stg[18 * 32];
+    L.sp = 0;
+    L.ng = make_uint2(sc.single_root, 0x80000000u);
+    L.tg = make_uint2(0u, 0u);
+    L.best.inst = 0xFFFFFFFFu, L.best.prim = 0xFFFFFFFFu, L.best.b1 = L.best.b2 = L.best.t = 0.f;
+    staged = false;
+    active = true;
+  };
   for (;;) {
-    // ---- refill idle lanes from the queue
-    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !active);
+    // ---- refill from the queue: idle lanes directly, or (STAGE) the empty prepared-ray slots
+    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, STAGE ? !staged : !active);
     if (!exhausted && idle) {
       const uint32_t n_idle = __popc(idle), avail = w_end - w_next;
       uint32_t i = w_next + __popc(idle & lt);
@@ -357,7 +384,23 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
       } else {
         w_next += n_idle;
       }
-      if (!active && i < count) {
+      if (STAGE) {
+        if (!staged && i < count) {
+          float3 o, d;
+          float t0, t1;
+          const uint32_t g = pol.load(i, o, d, t0, t1);
+          RaySpace rs;
+          setup_space(rs, o, d);
+          setup_shear(rs, d);
+          stg[0 * 32] = __float_as_uint(o.x), stg[1 * 32] = __float_as_uint(o.y), stg[2 * 32] = __float_as_uint(o.z);
+          stg[3 * 32] = __float_as_uint(rs.idir.x), stg[4 * 32] = __float_as_uint(rs.idir.y), stg[5 * 32] = __float_as_uint(rs.idir.z);
+          stg[6 * 32] = __float_as_uint(rs.sx.x), stg[7 * 32] = __float_as_uint(rs.sx.y), stg[8 * 32] = __float_as_uint(rs.sx.z);
+          stg[9 * 32] = __float_as_uint(rs.sy.x), stg[10 * 32] = __float_as_uint(rs.sy.y), stg[11 * 32] = __float_as_uint(rs.sy.z);
+          stg[12 * 32] = __float_as_uint(rs.sz.x), stg[13 * 32] = __float_as_uint(rs.sz.y), stg[14 * 32] = __float_as_uint(rs.sz.z);
+          stg[15 * 32] = __float_as_uint(t0), stg[16 * 32] = __float_as_uint(t1), stg[17 * 32] = i, stg[18 * 32] = g;
+          staged = true;
+        }
+      } else if (!active && i < count) {
         float3 o, d;
         float t0, t1;
         tag = pol.load(i, o, d, t0, t1);
@@ -367,7 +410,11 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
       }
       if (w_next >= count) exhausted = true;
     }
-    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) break;
+    if (STAGE && !active && staged) take_staged();
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
+      if (!STAGE || (exhausted && __ballot_sync(0xFFFFFFFFu, staged) == 0u)) break;
+      continue;
+    }
     // ---- traverse until enough lanes have finished to make a refill worthwhile
     for (;;) {
       // pop / leave instance / terminate; lanes holding only a postponed triangle group swap it under the next
@@ -381,6 +428,7 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
           if (L.sp == 0) {
             pol.commit(ray, tag, L.best.inst != 0xFFFFFFFFu, L.best);
             active = false;
+            if (STAGE && staged) take_staged();
           } else {
             const uint2 e = lane_pop(L, stack);
             if (e.y > 0x00FFFFFFu) L.ng = e;
@@ -407,10 +455,15 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
           if (want_tri && lane_triangle_step<ANY, COUNT, SINGLE>(L, sc, n_tris)) {
             pol.commit(ray, tag, true, L.best);
             active = false;
+            if (STAGE && staged) take_staged();
           }
         }
       }
-      if (!exhausted && 32u - __popc(m_act) >= sc.refill_lanes) break;
+      if (STAGE) {
+        if (!exhausted && (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, !staged)) >= sc.stage_lanes) break;
+      } else if (!exhausted && 32u - __popc(m_act) >= sc.refill_lanes) {
+        break;
+      }
     }
   }
   if (COUNT) {
