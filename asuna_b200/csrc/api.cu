@@ -460,9 +460,17 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   for (auto& in : ctx->instances) uses[in.mesh]++;
   bool flatten = true;
   if (const char* f = getenv("ASUNA_FLATTEN")) flatten = atoi(f) != 0;
+  // Instanced meshes are flattened too (one world-space copy per instance) while the whole scene stays under a triangle
+  // budget: 180 GB of HBM buy single-level traversal where a Vulkan driver instances to save memory.  48 B per triangle
+  // slot + ~12 B of nodes: the default 64 M triangles are 4 GB (plus the builder's scratch); ASUNA_FLATTEN_MAX_TRIS=0
+  // restricts flattening to single-use meshes.
+  uint64_t flat_budget = 64ull << 20, instanced_tris = 0;
+  if (const char* f = getenv("ASUNA_FLATTEN_MAX_TRIS")) flat_budget = strtoull(f, nullptr, 10);
+  for (auto& in : ctx->instances) instanced_tris += ctx->meshes[in.mesh].n_tris;
+  const bool flatten_all = flatten && instanced_tris <= flat_budget && instanced_tris < (1u << 27);
   std::vector<uint32_t> merged, tlas_ids;  // instance ids in the world BLAS / instance records under the top level
   for (uint32_t i = 0; i < n_inst; i++)
-    (flatten && uses[ctx->instances[i].mesh] == 1 ? merged : tlas_ids).push_back(i);
+    (flatten && (flatten_all || uses[ctx->instances[i].mesh] == 1) ? merged : tlas_ids).push_back(i);
   if (merged.size() == 1 && !tlas_ids.empty()) tlas_ids.push_back(merged[0]), merged.clear();  // nothing to merge with
   std::vector<char> mesh_merged(n_mesh, 0);
   for (uint32_t i : merged) mesh_merged[ctx->instances[i].mesh] = 1;
@@ -477,9 +485,8 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   uint32_t max_prims = n_tlas, world_tris = 0;
   for (uint32_t i = 0; i < n_mesh; i++) {
     HostMesh& m = ctx->meshes[i];
-    if (mesh_merged[i]) {
+    if (mesh_merged[i]) {  // lives in the world BLAS only (one copy per instance, counted below)
       m.node_base = m.tri_base = -1;
-      world_tris += m.n_tris;
       continue;
     }
     m.node_base = (int)total_nodes;
@@ -489,6 +496,7 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
     max_prims = std::max(max_prims, m.n_tris);
   }
   const size_t world_node_base = total_nodes, world_tri_base = total_tris;
+  for (uint32_t i : merged) world_tris += ctx->meshes[ctx->instances[i].mesh].n_tris;
   if (have_world) {
     total_nodes += std::max<uint32_t>(world_tris - 1, 1);
     total_tris += world_tris;
@@ -625,6 +633,7 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   ctx->view.world_inst = have_world ? n_inst : 0xFFFFFFFFu;
   ctx->view.single_root = single_level ? (uint32_t)world_node_base : 0xFFFFFFFFu;
   free_dev(d_soup);
+  if (ctx->scratch.capacity > (4u << 20)) ctx->scratch.release();  // ~330 B per primitive: give large builds' temporaries back
   ctx->view.magic = 0x4B000000u;
   ctx->view.refill_lanes = 8, ctx->view.tri_vote_shift = 2;
   ctx->view.stage_lanes = 16;

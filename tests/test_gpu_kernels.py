@@ -83,32 +83,52 @@ SCENE_BUILDERS = [
 ]
 
 
+# acceleration-structure policies of asuna_build_accel: plain two-level / single-use meshes flattened (instanced ones
+# keep their BLAS under the instance level next to the world BLAS) / everything flattened (default under the budget)
+ACCEL_POLICIES = {"two-level": {"ASUNA_FLATTEN": "0"}, "singles": {"ASUNA_FLATTEN": "1", "ASUNA_FLATTEN_MAX_TRIS": "0"},
+                  "all": {"ASUNA_FLATTEN": "1"}}
+
+
+def _set_policy(monkeypatch, name):
+    monkeypatch.delenv("ASUNA_FLATTEN", raising=False)
+    monkeypatch.delenv("ASUNA_FLATTEN_MAX_TRIS", raising=False)
+    for k, v in ACCEL_POLICIES[name].items():
+        monkeypatch.setenv(k, v)
+
+
 @pytest.mark.parametrize("builder", SCENE_BUILDERS)
 def test_flattening_does_not_change_hits(product_lib, builder, monkeypatch):
-    """Single-use instances are pre-transformed into one world-space BLAS (api.cu); against the plain two-level
-    structure (ASUNA_FLATTEN=0) the nearest hits must be the same primitives at the same distance."""
+    """Instances are pre-transformed into one world-space BLAS (api.cu); against the plain two-level structure
+    (ASUNA_FLATTEN=0) the nearest hits must be the same primitives at the same distance, whichever policy applies."""
     from asuna_b200 import capi
     sc = builder()
     rays = _random_rays(sc, 100000, 9)
-    out = []
-    for flag in ("0", "1"):
-        monkeypatch.setenv("ASUNA_FLATTEN", flag)
+    out = {}
+    for name in ACCEL_POLICIES:
+        _set_policy(monkeypatch, name)
         ctx = capi.Context(product_lib, 0)
         sc.upload(ctx)
-        out.append(ctx.trace_rays(rays) + (ctx.occlusion_rays(rays),))
+        out[name] = ctx.trace_rays(rays) + (ctx.occlusion_rays(rays), ctx.accel_stats())
         ctx.close()
-    (t0, i0, o0), (t1, i1, o1) = out
-    same = (i0 == i1).all(axis=1)
-    tie = ~same & (np.abs(t0[:, 0] - t1[:, 0]) <= 1e-5 * np.maximum(1.0, np.abs(t0[:, 0])))
-    assert (same | tie).mean() >= 0.9995, (same.mean(), tie.mean())
-    hit = same & (i0[:, 0] != 0xFFFFFFFF)
-    assert hit.mean() > 0.2
-    assert (np.abs(t0[hit, 0] - t1[hit, 0]) / np.maximum(1.0, t0[hit, 0])).max() <= 1e-5
-    assert (o0 == o1).mean() >= 0.9995
+    t0, i0, o0, a0 = out["two-level"]
+    assert a0["tlas_nodes"] >= 1
+    for name in ("singles", "all"):
+        t1, i1, o1, _ = out[name]
+        same = (i0 == i1).all(axis=1)
+        tie = ~same & (np.abs(t0[:, 0] - t1[:, 0]) <= 1e-5 * np.maximum(1.0, np.abs(t0[:, 0])))
+        assert (same | tie).mean() >= 0.9995, (name, same.mean(), tie.mean())
+        hit = same & (i0[:, 0] != 0xFFFFFFFF)
+        assert hit.mean() > 0.2
+        assert (np.abs(t0[hit, 0] - t1[hit, 0]) / np.maximum(1.0, t0[hit, 0])).max() <= 1e-5
+        assert (o0 == o1).mean() >= 0.9995
+    n_inst_tris = sum(len(sc.meshes[m][1]) // 3 for _, m, _, _ in sc.instances)
+    assert out["all"][3]["leaf_prims"] == n_inst_tris  # one world-space copy per instance
 
 
+@pytest.mark.parametrize("policy", ["all", "singles"])
 @pytest.mark.parametrize("builder", SCENE_BUILDERS)
-def test_traversal_matches_oracle_on_random_rays(gpu_ctx, cpu_ctx, builder):
+def test_traversal_matches_oracle_on_random_rays(gpu_ctx, cpu_ctx, builder, policy, monkeypatch):
+    _set_policy(monkeypatch, policy)  # read by asuna_build_accel (sc.upload)
     sc = builder()
     sc.upload(gpu_ctx)
     sc.upload(cpu_ctx)

@@ -74,6 +74,16 @@ def test_render_parity(name, gpu_ctx, cpu_ctx):
     compare(SCENES[name](), gpu_ctx, cpu_ctx)
 
 
+@pytest.mark.parametrize("policy", [{"ASUNA_FLATTEN": "0"}, {"ASUNA_FLATTEN": "1", "ASUNA_FLATTEN_MAX_TRIS": "0"}])
+@pytest.mark.parametrize("name", ["instanced_field", "materials_all_lights"])
+def test_render_parity_two_level(name, policy, gpu_ctx, cpu_ctx, monkeypatch):
+    """By default asuna_build_accel flattens every instance under its triangle budget (single-level kernels); the
+    two-level kernels (plain, and with the world BLAS of the single-use meshes as one of the instances) stay covered."""
+    for k, v in policy.items():
+        monkeypatch.setenv(k, v)  # read by asuna_build_accel
+    compare(SCENES[name](), gpu_ctx, cpu_ctx)
+
+
 def test_depth_of_field_and_opencv_cameras(gpu_ctx, cpu_ctx, product_lib, oracle_lib):
     from asuna_b200 import capi
     from oracle.binding import OracleContext
