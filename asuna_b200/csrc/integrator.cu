@@ -310,7 +310,12 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
     p.nee = false;
     if (valid) {
       slot = queue[i];
-      float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot], th = ps.thr[slot], ra = ps.rad[slot];
+      // the delta shaders (dielectric, conductor, mirror) neither read nor change the path radiance: 32 B less per hit
+      constexpr bool kRadiance = !(KIND == kKindMaterial0 + ASUNA_MAT_DIELECTRIC || KIND == kKindMaterial0 + ASUNA_MAT_CONDUCTOR ||
+                                   KIND == kKindMaterial0 + ASUNA_MAT_MIRROR);
+      float4 ro = ps.ray_o[slot], rd = ps.ray_d[slot], th = ps.thr[slot];
+      float4 ra = make_float4(0.f, 0.f, 0.f, 0.f);
+      if constexpr (kRadiance) ra = ps.rad[slot];
       uint32_t fi = slot / fp.n_pixels, pixel = slot - fi * fp.n_pixels;
       bool frame0 = fp.frame_ids[fi] == 0;
       for (int c = 0; c < ASUNA_NUM_OUTPUT_IMAGES - 1; c++) se.aov[c] = frame0 ? out.img[c + 1] : nullptr;
@@ -354,7 +359,9 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
       int next_depth = p.depth + 1;
       cont = !p.stop && next_depth <= fp.pc.maxPathDepth;
       incoherent = cont && next_depth >= 2;
-      ps.rad[slot] = make_float4(p.radiance.x, p.radiance.y, p.radiance.z, ra.w);
+      if constexpr (kRadiance)
+        if (p.radiance.x != ra.x || p.radiance.y != ra.y || p.radiance.z != ra.z)
+          ps.rad[slot] = make_float4(p.radiance.x, p.radiance.y, p.radiance.z, ra.w);
       if (cont) {
         ps.ray_o[slot] = make_float4(p.ray_o.x, p.ray_o.y, p.ray_o.z, __uint_as_float(p.seed));
         ps.ray_d[slot] = make_float4(p.ray_d.x, p.ray_d.y, p.ray_d.z, p.bsdf_pdf);
