@@ -89,7 +89,7 @@ struct asuna_ctx {
   Totals* h_totals = nullptr;  // pinned
   bool counting = false;
   uint32_t path_capacity = 0;
-  uint32_t max_batch_frames = 8;
+  uint32_t max_batch_frames = ASUNA_MAX_BATCH_FRAMES;  // capped below so that a batch stays under ~16 M paths (8 frames at 1080p, 64 at 512x512)
   LaunchDims dims;
 
   // user-ray scratch

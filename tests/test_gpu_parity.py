@@ -147,6 +147,22 @@ def test_closed_forms_on_gpu(gpu_ctx):
     assert np.allclose(img[16, 16, :3], [10, 10, 4], atol=1e-4)
 
 
+def test_pinned_read_back_equals_pageable(gpu_ctx):
+    """asuna_host_alloc hands out page-locked buffers for asuna_read_channel (≙ the mapped staging buffer of
+    tracer.cpp:317-336); the image must be the one a plain host pointer receives."""
+    sc = scenes.cornell(48, 40, spp=2, depth=3)
+    sc.upload(gpu_ctx)
+    imgs = sc.render_shot(gpu_ctx, 0)
+    pinned = gpu_ctx.pinned_image()
+    assert pinned.shape == (40, 48, 4) and pinned.dtype == np.float32
+    for ch in (0, 1, 8):
+        got = gpu_ctx.read_channel(ch, out=pinned)
+        assert got is pinned
+        ref = gpu_ctx.read_channel(ch)
+        assert np.array_equal(pinned, ref, equal_nan=True)
+    assert np.array_equal(gpu_ctx.read_channel(0), imgs[0], equal_nan=True)
+
+
 def test_error_behaviour(gpu_ctx):
     from asuna_b200 import capi, structs as S
     with pytest.raises(capi.AsunaError):
