@@ -185,15 +185,75 @@ __global__ void __launch_bounds__(kThreads) k_sort_hist(const uint64_t* __restri
   hist[threadIdx.x * n_blocks + blockIdx.x] = h[threadIdx.x];
 }
 
+// One block per digit: exclusive scan of that digit's per-block counts in place (row d of hist), row total to
+// totals[d].  The digit bases (exclusive scan of the 256 totals) are recomputed by every scatter block, so the pass
+// needs no serial walk over the whole 256 x blocks table.
+__global__ void __launch_bounds__(kThreads) k_sort_scan_rows(uint32_t* __restrict__ hist, uint32_t n_blocks,
+                                                             uint32_t* __restrict__ totals) {
+  __shared__ uint32_t warp_sums[2][kThreads / 32];
+  uint32_t* row = hist + (size_t)blockIdx.x * n_blocks;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t carry = 0;
+  int buf = 0;
+  for (uint32_t base = 0; base < n_blocks; base += kThreads * 4, buf ^= 1) {
+    const uint32_t i0 = base + threadIdx.x * 4;
+    uint32_t v[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) v[k] = i0 + k < n_blocks ? row[i0 + k] : 0u, sum += v[k];
+    uint32_t sc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, sc, o);
+      if (lane >= o) sc += t;
+    }
+    if (lane == 31) warp_sums[buf][warp] = sc;
+    __syncthreads();
+    uint32_t before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) {
+      const uint32_t x = warp_sums[buf][w];
+      before += w < warp ? x : 0u;
+      all += x;
+    }
+    uint32_t run = carry + before + sc - sum;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (i0 + k < n_blocks) row[i0 + k] = run;
+      run += v[k];
+    }
+    carry += all;
+  }
+  if (threadIdx.x == 0) totals[blockIdx.x] = carry;
+}
+
 __global__ void __launch_bounds__(kThreads) k_sort_scatter(const uint64_t* __restrict__ keys_in,
                                                             const uint32_t* __restrict__ vals_in,
                                                             uint64_t* __restrict__ keys_out,
                                                             uint32_t* __restrict__ vals_out, uint32_t n, int shift,
-                                                            const uint32_t* __restrict__ hist, uint32_t n_blocks) {
+                                                            const uint32_t* __restrict__ hist, uint32_t n_blocks,
+                                                            const uint32_t* __restrict__ totals) {
   constexpr int kWarps = kThreads / 32;
   constexpr int kRounds = kSortTile / kWarps / 32;  // 16
   __shared__ uint32_t wh[kWarps][256];
+  __shared__ uint32_t digit_sums[kWarps];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // base of digit `threadIdx.x` = number of keys with a smaller digit (exclusive scan of the 256 digit totals)
+  uint32_t digit_base;
+  {
+    const uint32_t t = totals[threadIdx.x];
+    uint32_t sc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t u = __shfl_up_sync(0xFFFFFFFFu, sc, o);
+      if (lane >= o) sc += u;
+    }
+    if (lane == 31) digit_sums[warp] = sc;
+    __syncthreads();
+    uint32_t before = 0;
+#pragma unroll
+    for (int w = 0; w < kWarps; w++) before += w < warp ? digit_sums[w] : 0u;
+    digit_base = before + sc - t;
+  }
   for (int b = threadIdx.x; b < kWarps * 256; b += kThreads) (&wh[0][0])[b] = 0;
   __syncthreads();
   uint32_t wbase = blockIdx.x * kSortTile + warp * (kRounds * 32);
@@ -210,7 +270,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const uint64_t* __res
   // per digit: global base of this block, then exclusive over the warps of the block
   {
     uint32_t bin = threadIdx.x;
-    uint32_t run = hist[bin * n_blocks + blockIdx.x];
+    uint32_t run = digit_base + hist[bin * n_blocks + blockIdx.x];
 #pragma unroll
     for (int w = 0; w < kWarps; w++) {
       uint32_t c = wh[w][bin];
@@ -734,7 +794,7 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
   A(keys[1], sizeof(uint64_t) * cap);
   A(vals[0], sizeof(uint32_t) * cap);
   A(vals[1], sizeof(uint32_t) * cap);
-  A(hist, sizeof(uint32_t) * 256 * (size_t)div_up(cap, kSortTile));
+  A(hist, sizeof(uint32_t) * 256 * ((size_t)div_up(cap, kSortTile) + 1));  // [256][blocks] + the 256 digit totals
   A(children, sizeof(int2) * cap);
   A(nlo, sizeof(float4) * 2 * (size_t)cap);
   A(nhi, sizeof(float4) * 2 * (size_t)cap);
@@ -779,9 +839,10 @@ static void sort_passes(cudaStream_t s, uint32_t n, BuildScratch& sc) {
   int cur = 0;
   for (int shift = 0; shift < 64; shift += 8) {
     k_sort_hist<<<sort_blocks, kThreads, 0, s>>>(sc.keys[cur], n, shift, sc.hist, sort_blocks);
-    k_scan_exclusive<<<1, 1024, 0, s>>>(sc.hist, 256u * sort_blocks);
+    uint32_t* totals = sc.hist + 256u * (size_t)sort_blocks;
+    k_sort_scan_rows<<<256, kThreads, 0, s>>>(sc.hist, sort_blocks, totals);
     k_sort_scatter<<<sort_blocks, kThreads, 0, s>>>(sc.keys[cur], sc.vals[cur], sc.keys[cur ^ 1], sc.vals[cur ^ 1],
-                                                    n, shift, sc.hist, sort_blocks);
+                                                    n, shift, sc.hist, sort_blocks, totals);
     cur ^= 1;
   }
   // 8 passes: the result is back in buffer 0
