@@ -173,6 +173,12 @@ def main():
     if args.impl == "reference":
         return run_reference_arm(args)
 
+    # stdout carries exactly one JSON line: native libraries (NCCL prints its version banner there under
+    # NCCL_DEBUG=VERSION/WARN/INFO) get stderr as their fd 1 for the whole run, the JSON goes to the saved descriptor
+    sys.stdout.flush()
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from asuna_b200 import capi
@@ -182,8 +188,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"  # the version banner goes to stdout; stdout carries exactly one JSON line
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     else:
@@ -320,7 +324,8 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_run(args, 64, 1, budget_s=args.cpu_budget_s)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line))
+        json_out.write(json.dumps(line) + "\n")
+        json_out.flush()
     ctx.close()
     if world > 1:
         dist.barrier()
