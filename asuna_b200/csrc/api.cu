@@ -635,7 +635,7 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   free_dev(d_soup);
   if (ctx->scratch.capacity > (4u << 20)) ctx->scratch.release();  // ~330 B per primitive: give large builds' temporaries back
   ctx->view.magic = 0x4B000000u;
-  ctx->view.refill_lanes = 8, ctx->view.tri_vote_shift = 2;
+  ctx->view.refill_lanes = 8, ctx->view.tri_vote_shift = 3;
   ctx->view.stage_lanes = 16;
   if (const char* t = getenv("ASUNA_STAGE_LANES")) ctx->view.stage_lanes = std::min(std::max(atoi(t), 1), 32);
   if (const char* t = getenv("ASUNA_TUNE")) {  // "refill,shift[,cost_prim x10]" -- traversal tuning experiments

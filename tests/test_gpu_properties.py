@@ -74,3 +74,18 @@ def test_full_size_partition_invariance(full_scene, product_lib):
     for ctx, _ in parts:
         ctx.close()
     single.close()
+
+
+def test_small_film_batches_of_64_frames_equal_single_frames(product_lib):
+    """Small films are rendered up to 64 frames per batch (api.cu, asuna_render_frames); the running mean must not
+    depend on how the frames were grouped: 70 frames in one call = 70 calls of one frame, bit for bit."""
+    sc = scenes.cornell(64, 48, spp=70, depth=4)
+    a = _render(sc, product_lib, [70])
+    b = _render(sc, product_lib, [1] * 70)
+    c = _render(sc, product_lib, [64, 6])
+    ia = a.read_channel(0)
+    assert np.array_equal(ia, b.read_channel(0)) and np.array_equal(ia, c.read_channel(0))
+    assert np.array_equal(a.read_channel(8), b.read_channel(8))
+    assert a.stats()["paths"] == 70 * 64 * 48
+    for x in (a, b, c):
+        x.close()
