@@ -10,7 +10,7 @@
 //
 // Execution model: persistent warps.  Every lane owns one ray at a time; the warp loops over
 //   pop / leave instance / terminate  ->  one wide-node step  ->  instance entry  ->  one triangle step
-// where the triangle step only runs when a quarter of the live lanes want it (or nothing else is left):
+// where the triangle step only runs when an eighth of the live lanes want it (SceneView::tri_vote_shift) (or nothing else is left):
 // lanes with a pending triangle group swap it under the next node group of their stack and keep
 // traversing ("triangle postponing", Ylitie et al. 2017 section 5).  Finished lanes are refilled from the
 // ray queue with one atomic per warp as soon as `refill_lanes` of them are idle.
