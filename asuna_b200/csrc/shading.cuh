@@ -123,12 +123,18 @@ ADEV int wrap_index(int i, int n) {
   int m = i % n;
   return m < 0 ? m + n : m;
 }
-ADEV float4 tex_bilinear(const DTexture& t, float u, float v) {
+// Not inlined: the textured shaders call it from up to nine places, and inlined copies (float and integer
+// remainders) made up 28 % of the 10 k-instruction PBR kernel, which was stalling on instruction fetch.
+ADEV int wrap_coord(float f0, int n) {  // f0 = floorf(coordinate): its remainder modulo n in [0, n)
+  // |f0| < 2^30 converts to int exactly, so the float remainder of the general path is only needed beyond that
+  return fabsf(f0) < 1073741824.0f ? wrap_index((int)f0, n) : wrap_index((int)fmodf(f0, (float)n), n);
+}
+__device__ __noinline__ float4 tex_bilinear(const DTexture& t, float u, float v) {
   float x = u * (float)t.w - 0.5f, y = v * (float)t.h - 0.5f;
   if (!isfinite(x) || !isfinite(y)) return make_float4(0, 0, 0, 0);
   float fx0 = floorf(x), fy0 = floorf(y);
   float fx = x - fx0, fy = y - fy0;
-  int x0 = wrap_index((int)fmodf(fx0, (float)t.w), t.w), y0 = wrap_index((int)fmodf(fy0, (float)t.h), t.h);
+  int x0 = wrap_coord(fx0, t.w), y0 = wrap_coord(fy0, t.h);
   int x1 = wrap_index(x0 + 1, t.w), y1 = wrap_index(y0 + 1, t.h);
   float4 p00 = __ldg(&t.texels[(size_t)y0 * t.w + x0]), p10 = __ldg(&t.texels[(size_t)y0 * t.w + x1]);
   float4 p01 = __ldg(&t.texels[(size_t)y1 * t.w + x0]), p11 = __ldg(&t.texels[(size_t)y1 * t.w + x1]);
