@@ -74,8 +74,9 @@ struct asuna_ctx {
   // frame state
   AsunaCamera cam{};
   AsunaSunSky sunsky{};
-  float sky_ground_irrad[3] = {0.f, 0.f, 0.f};  // of `sunsky`, evaluated on the device when it changes
-  bool sky_irrad_valid = false;
+  SkyPre sky{};  // the per-setting part of the sun & sky model for `sunsky`, evaluated on the device when it changes
+  SkyPre* d_sky = nullptr;
+  bool sky_valid = false;
   AsunaState pc{};
   uint32_t rank = 0, world = 1;
   bool have_accum = false;
@@ -247,7 +248,7 @@ FrameParams make_frame_params(asuna_ctx* ctx) {
   FrameParams fp{};
   fp.cam = ctx->cam;
   fp.sunsky = ctx->sunsky;
-  for (int k = 0; k < 3; k++) fp.sky_ground_irrad[k] = ctx->sky_ground_irrad[k];
+  fp.sky = ctx->sky;
   fp.pc = ctx->pc;
   fp.width = ctx->W;
   fp.height = ctx->H;
@@ -296,7 +297,7 @@ int asuna_create(asuna_ctx** out, int gpu_id) {
   ctx->sm_count = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&ctx->d_counters, sizeof(Counters)) != cudaSuccess ||
-      cudaMalloc(&ctx->d_totals, 2 * sizeof(Totals))  /* [1] = scratch for small device->host results */ != cudaSuccess ||
+      cudaMalloc(&ctx->d_totals, sizeof(Totals)) != cudaSuccess ||
       cudaMemset(ctx->d_totals, 0, sizeof(Totals)) != cudaSuccess ||
       cudaMallocHost(&ctx->h_totals, sizeof(Totals)) != cudaSuccess ||
       query_launch_dims(ctx->dims, ctx->sm_count) != cudaSuccess) {
@@ -331,6 +332,7 @@ void asuna_destroy(asuna_ctx* ctx) {
   free_dev(ctx->d_partial);
   free_dev(ctx->d_counters);
   free_dev(ctx->d_totals);
+  free_dev(ctx->d_sky);
   free_dev(ctx->d_user_rays);
   free_dev(ctx->d_user_tuv);
   free_dev(ctx->d_user_ip);
@@ -665,13 +667,14 @@ int asuna_set_sunsky(asuna_ctx* ctx, const AsunaSunSky* s) {
   if (!s) return fail(ctx, ASUNA_E_INVALID, "null sunsky");
   const bool changed = memcmp(&ctx->sunsky, s, sizeof *s) != 0;
   ctx->sunsky = *s;
-  if (s->in_use == 1 && (changed || !ctx->sky_irrad_valid)) {
-    // the model's ground irradiance depends on the sun setting only: one device evaluation per setting, not per lookup
+  if (s->in_use == 1 && (changed || !ctx->sky_valid)) {
+    // most of the model depends on the setting only: one device evaluation per setting, not per lookup
     cudaSetDevice(ctx->device);
-    launch_sky_ground_irradiance(ctx->stream, ctx->sunsky, reinterpret_cast<float*>(ctx->d_totals + 1));
-    ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->sky_ground_irrad, ctx->d_totals + 1, 3 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    if (!ctx->d_sky) ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_sky, sizeof(SkyPre)));
+    launch_sky_prepare(ctx->stream, ctx->sunsky, ctx->d_sky);
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(&ctx->sky, ctx->d_sky, sizeof(SkyPre), cudaMemcpyDeviceToHost, ctx->stream));
     ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
-    ctx->sky_irrad_valid = true;
+    ctx->sky_valid = true;
   }
   return 0;
 }

@@ -137,6 +137,15 @@ struct Totals {
   unsigned long long lane_stats[6];
 };
 
+// Sun & sky model: the per-setting part of sun_and_sky (shading.cuh), evaluated on the device once per setting.
+struct SkyPre {
+  float rgb_scale[3], sat, horiz, haze, factor;
+  float sun[3], real_sun[3], sun_color_up[3], sun_color_down[3];
+  float sun_radius, disk_scale, glow_scale;
+  float lum0, zx, zy, perez[3][5], perez_den[3];  // sky luminance / chromaticity coefficients for T = haze
+  float ground_irrad[3];                           // calc_irrad
+};
+
 struct FrameParams {
   AsunaCamera cam;
   AsunaSunSky sunsky;
@@ -146,7 +155,7 @@ struct FrameParams {
   uint32_t n_frames;                 // frames in this batch
   int32_t frame_ids[64];             // curFrame value of each batch frame
   uint32_t first_is_replace;         // first frame of the batch replaces the accumulation buffer
-  float sky_ground_irrad[3];         // sun & sky: calc_irrad of the current sun setting (shading.cuh sky_ground_irradiance)
+  SkyPre sky;                        // sun & sky: what depends on the setting only (shading.cuh sky_prepare)
 };
 #define ASUNA_MAX_BATCH_FRAMES 64
 

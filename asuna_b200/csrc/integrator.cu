@@ -113,10 +113,11 @@ k_trace_user(const __grid_constant__ SceneView sc, UserPolicy pol, uint32_t n, u
   trace_persistent<ANY, false, SINGLE, false>(sc, pol, n, ticket, &cnt->stack_overflow, nullptr, nullptr);
 }
 
-// Sun & sky: the ground irradiance of the current sun setting, once per setting instead of once per lookup.
-__global__ void k_sky_ground_irradiance(AsunaSunSky ss, float* out) {
-  const float3 v = sky_ground_irradiance(ss);
-  out[0] = v.x, out[1] = v.y, out[2] = v.z;
+// Sun & sky: everything that depends on the setting only, once per setting instead of once per lookup.
+__global__ void k_sky_prepare(AsunaSunSky ss, SkyPre* out) {
+  SkyPre p;
+  sky_prepare(ss, p);
+  *out = p;
 }
 
 // Adds one batch's per-iteration counters into the persistent totals (one thread; a few hundred words).
@@ -479,8 +480,8 @@ void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView&
     else k_trace_closest<false, false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter, qsel);
   }
 }
-void launch_sky_ground_irradiance(cudaStream_t s, const AsunaSunSky& ss, float* out3) {
-  k_sky_ground_irradiance<<<1, 1, 0, s>>>(ss, out3);
+void launch_sky_prepare(cudaStream_t s, const AsunaSunSky& ss, SkyPre* out) {
+  k_sky_prepare<<<1, 1, 0, s>>>(ss, out);
 }
 void launch_fold_counters(cudaStream_t s, const Counters* cnt, Totals* tot, int iters) {
   k_fold_counters<<<1, 1, 0, s>>>(cnt, tot, iters);

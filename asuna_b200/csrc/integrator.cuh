@@ -20,7 +20,7 @@ void launch_raygen(cudaStream_t s, const FrameParams& fp, const PathState& ps, c
 void launch_trace_closest(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
                           int iter, int qsel, bool counting);
 void launch_fold_counters(cudaStream_t s, const Counters* cnt, Totals* tot, int iters);
-void launch_sky_ground_irradiance(cudaStream_t s, const AsunaSunSky& ss, float* out3_device);
+void launch_sky_prepare(cudaStream_t s, const AsunaSunSky& ss, SkyPre* out_device);
 int launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const FrameParams& fp, const PathState& ps,
                  const OutputImages& out, Counters* cnt, int iter, int qsel, uint32_t kind_mask, uint32_t n_paths);
 void launch_trace_shadow(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,

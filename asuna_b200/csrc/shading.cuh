@@ -151,10 +151,14 @@ struct PerezCoeffs {
   float A, B, C, D, E;
 };
 // one evaluator for the Perez form the reference spells out at :174-177, :185-188 and :220-223
+ADEV float perez_num(PerezCoeffs k, float cos_theta, float gamma, float cos_gamma) {
+  return (1.0f + k.A * expf(k.B / cos_theta)) * (1.0f + k.C * expf(k.D * gamma) + k.E * cos_gamma * cos_gamma);
+}
+ADEV float perez_den(PerezCoeffs k, float theta_s, float cos_theta_s) {  // depends on the sun only
+  return (1.0f + k.A * expf(k.B / 1.0f)) * (1.0f + k.C * expf(k.D * theta_s) + k.E * cos_theta_s * cos_theta_s);
+}
 ADEV float perez_ratio(PerezCoeffs k, float cos_theta, float gamma, float cos_gamma, float theta_s, float cos_theta_s) {
-  float num = (1.0f + k.A * expf(k.B / cos_theta)) * (1.0f + k.C * expf(k.D * gamma) + k.E * cos_gamma * cos_gamma);
-  float den = (1.0f + k.A * expf(k.B / 1.0f)) * (1.0f + k.C * expf(k.D * theta_s) + k.E * cos_theta_s * cos_theta_s);
-  return num / den;
+  return perez_num(k, cos_theta, gamma, cos_gamma) / perez_den(k, theta_s, cos_theta_s);
 }
 // :228-243 with :201-226 and :134-199 folded in
 ADEV float3 sky_env_color(float3 sun, float3 dir, float T) {
@@ -259,71 +263,131 @@ ADEV float3 sky_ground_irradiance(const AsunaSunSky& ss) {
   irrad /= 25.0f;
   return irrad;
 }
-// :405-533
-__device__ __noinline__ float3 sun_and_sky(const AsunaSunSky& ss, float3 in_dir, float3 ground_irrad) {
-  float factor = 1.0f, night_factor = 1.0f;
-  float3 rgb_scale = f3(ss.rgb_unit_conversion);
-  float horiz = ss.horizon_height / 10.0f;
-  float3 dir = tweak_vector(in_dir, ss.y_is_up, horiz);
-  float haze = fmaxf(2.0f + ss.haze, 2.0f);
-  float sat;
+// Everything of the model that depends on the AsunaSunSky setting only (:134-243 sky coefficients for T = haze,
+// :108-132 sun colours, :264-276 saturation, :312-394 disk / glow scales, :245-262 ground irradiance): filled once per
+// setting by k_sky_prepare (integrator.cu) with the same expressions sun_and_sky evaluates, then read by every lookup.
+ADEV void sky_prepare(const AsunaSunSky& ss, SkyPre& p) {
+  p.horiz = ss.horizon_height / 10.0f;
+  p.haze = fmaxf(2.0f + ss.haze, 2.0f);
   {  // tweak_saturation :264-276
     float s = ss.saturation;
     if (s <= 1.0f) {
-      float h = clampf((haze - 2.0f) / 15.0f, 0.0f, 1.0f);
+      float h = clampf((p.haze - 2.0f) / 15.0f, 0.0f, 1.0f);
       h = powf(h, 3.0f);
-      sat = (s * (1.0f - h)) + powf(s, 3.0f) * h;
+      p.sat = (s * (1.0f - h)) + powf(s, 3.0f) * h;
     } else
-      sat = 1.0f;
+      p.sat = 1.0f;
   }
+  float3 rgb_scale = f3(ss.rgb_unit_conversion);
   if (luminance(rgb_scale) < 0.0f) rgb_scale = f3(1.0f / 80000.0f);
   rgb_scale *= ss.multiplier;
+  p.rgb_scale[0] = rgb_scale.x, p.rgb_scale[1] = rgb_scale.y, p.rgb_scale[2] = rgb_scale.z;
+  float factor = 1.0f;
+  float3 real_sun;
+  const float3 sun = sun_vector(ss, p.horiz, factor, real_sun);
+  p.factor = factor;
+  p.sun[0] = sun.x, p.sun[1] = sun.y, p.sun[2] = sun.z;
+  p.real_sun[0] = real_sun.x, p.real_sun[1] = real_sun.y, p.real_sun[2] = real_sun.z;
+  const float3 up = sun_disk_color(sun, p.haze), down = sun_disk_color(sun, 2.0f);
+  p.sun_color_up[0] = up.x, p.sun_color_up[1] = up.y, p.sun_color_up[2] = up.z;
+  p.sun_color_down[0] = down.x, p.sun_color_down[1] = down.y, p.sun_color_down[2] = down.z;
+  p.sun_radius = 0.00465f * ss.sun_disk_scale * 10.0f;
+  p.disk_scale = 1.0f, p.glow_scale = 1.0f;
+  if (ss.physically_scaled_sun == 1) {  // calc_physical_scale :312-394
+    float disk_r = 0.00465f * ss.sun_disk_scale, glow_r = disk_r * 10.0f;
+    float glow_integral = ss.sun_glow_intensity * ((4.f * kSsPi) - (24.f * kSsPi) / (glow_r * glow_r) +
+                                                    (24.f * kSsPi) * sinf(glow_r) / (glow_r * glow_r * glow_r));
+    float target = ss.sun_disk_intensity * kSsPi;
+    float max_glow = 0.5f * target;
+    if (glow_integral > max_glow) {
+      p.glow_scale *= max_glow / glow_integral;
+      target -= max_glow;
+    } else
+      target -= glow_integral;
+    float area = 2 * kSsPi * (1 - cosf(disk_r));
+    float target_intensity = target / area;
+    float actual_intensity = ss.sun_disk_intensity * 100.0f * (1.0f * area) / area;
+    p.disk_scale = (target_intensity == 0.0f) ? 0.0f : target_intensity / actual_intensity;
+  }
+  {  // sky_env_color's sun-only part for T = haze
+    const float T = p.haze;
+    const float theta_s = acosf(sun.z);
+    const float chi = (4.0f / 9.0f - T / 120.0f) * (kSsPi - 2.0f * theta_s);
+    p.lum0 = 1000.0f * ((4.0453f * T - 4.9710f) * tanf(chi) - 0.2155f * T + 2.4192f);
+    const float t2 = T * T, ts2 = theta_s * theta_s, ts3 = ts2 * theta_s;
+    p.zx = ((+0.001650f * ts3 - 0.003742f * ts2 + 0.002088f * theta_s + 0) * t2 +
+            (-0.029028f * ts3 + 0.063773f * ts2 - 0.032020f * theta_s + 0.003948f) * T +
+            (+0.116936f * ts3 - 0.211960f * ts2 + 0.060523f * theta_s + 0.258852f));
+    p.zy = ((+0.002759f * ts3 - 0.006105f * ts2 + 0.003162f * theta_s + 0) * t2 +
+            (-0.042149f * ts3 + 0.089701f * ts2 - 0.041536f * theta_s + 0.005158f) * T +
+            (+0.153467f * ts3 - 0.267568f * ts2 + 0.066698f * theta_s + 0.266881f));
+    const PerezCoeffs kY = {0.178721f * T - 1.463037f, -0.355402f * T + 0.427494f, -0.022669f * T + 5.325056f,
+                            0.120647f * T - 2.577052f, -0.066967f * T + 0.370275f};
+    const PerezCoeffs kx = {-0.019257f * T - (0.29f - powf(sun.z, 0.5f) * 0.09f), -0.066513f * T + 0.000818f,
+                            -0.000417f * T + 0.212479f, -0.064097f * T - 0.898875f, -0.003251f * T + 0.045178f};
+    const PerezCoeffs ky = {-0.016698f * T - 0.260787f, -0.094958f * T + 0.009213f, -0.007928f * T + 0.210230f,
+                            -0.044050f * T - 1.653694f, -0.010922f * T + 0.052919f};
+    const PerezCoeffs* src[3] = {&kY, &kx, &ky};
+    for (int c = 0; c < 3; c++) {
+      p.perez[c][0] = src[c]->A, p.perez[c][1] = src[c]->B, p.perez[c][2] = src[c]->C, p.perez[c][3] = src[c]->D,
+      p.perez[c][4] = src[c]->E;
+      p.perez_den[c] = perez_den(*src[c], theta_s, sun.z);
+    }
+  }
+  const float3 irrad = sky_ground_irradiance(ss);
+  p.ground_irrad[0] = irrad.x, p.ground_irrad[1] = irrad.y, p.ground_irrad[2] = irrad.z;
+}
+// sky_env_color(sun, dir, haze) from the prepared coefficients: only the direction-dependent factors remain
+ADEV float3 sky_env_color_pre(const SkyPre& p, float3 sun, float3 dir) {
+  const PerezCoeffs kY = {p.perez[0][0], p.perez[0][1], p.perez[0][2], p.perez[0][3], p.perez[0][4]};
+  const PerezCoeffs kx = {p.perez[1][0], p.perez[1][1], p.perez[1][2], p.perez[1][3], p.perez[1][4]};
+  const PerezCoeffs ky = {p.perez[2][0], p.perez[2][1], p.perez[2][2], p.perez[2][3], p.perez[2][4]};
+  float lum = p.lum0;
+  const float cg_raw = dot(sun, dir);
+  {
+    float cg = cg_raw < 0.0f ? 0.0f : cg_raw;
+    if (cg > 1.0f) cg = 2.0f - cg;
+    lum *= perez_num(kY, dir.z, acosf(cg), cg) / p.perez_den[0];
+  }
+  const float cg = cg_raw > 1.0f ? 2.0f - cg_raw : cg_raw;
+  const float gamma = acosf(cg);
+  const float x = p.zx * (perez_num(kx, dir.z, gamma, cg) / p.perez_den[1]);
+  const float y = p.zy * (perez_num(ky, dir.z, gamma, cg) / p.perez_den[2]);
+  const float Y = lum, X = (x / y) * Y, Z = ((1.0f - x - y) / y) * Y;
+  return f3(3.241f * X - 1.537f * Y - 0.499f * Z, -0.969f * X + 1.876f * Y + 0.042f * Z,
+            0.056f * X - 0.204f * Y + 1.057f * Z) * kSsPi;
+}
+// :405-533 with the per-setting values taken from `p`
+__device__ __noinline__ float3 sun_and_sky(const AsunaSunSky& ss, const SkyPre& p, float3 in_dir) {
   if (ss.multiplier <= 0.0f) return f3(0.0f);
-  float downness = dir.z;
-  float3 real_dir = dir;
+  float night_factor = 1.0f;
+  const float factor = p.factor, haze = p.haze, sat = p.sat;
+  const float3 rgb_scale = f3(p.rgb_scale), sun = f3(p.sun), real_sun = f3(p.real_sun);
+  float3 dir = tweak_vector(in_dir, ss.y_is_up, p.horiz);
+  const float downness = dir.z;
+  const float3 real_dir = dir;
   if (dir.z < 0.001f) {
     dir.z = 0.001f;
     dir = normalize(dir);
   }
-  float3 real_sun;
-  float3 sun = sun_vector(ss, horiz, factor, real_sun);
   float3 tint = f3(0.0f);
   if (factor > 0.0f) {
-    tint = sky_env_color(sun, dir, haze);
+    tint = sky_env_color_pre(p, sun, dir);
     if (factor < 1.0f) tint *= factor;
   }
-  float3 sun_color = sun_disk_color(sun, downness > 0 ? haze : 2.0f);
+  const float3 sun_color = downness > 0 ? f3(p.sun_color_up) : f3(p.sun_color_down);
   if (ss.sun_disk_intensity > 0.0f && ss.sun_disk_scale > 0.0f) {
     float sun_angle = acosf(dot(real_dir, real_sun));
-    float sun_radius = 0.00465f * ss.sun_disk_scale * 10.0f;
-    if (sun_angle < sun_radius) {
-      float disk_scale = 1.0f, glow_scale = 1.0f;
-      if (ss.physically_scaled_sun == 1) {  // calc_physical_scale :312-394
-        float disk_r = 0.00465f * ss.sun_disk_scale, glow_r = disk_r * 10.0f;
-        float glow_integral = ss.sun_glow_intensity * ((4.f * kSsPi) - (24.f * kSsPi) / (glow_r * glow_r) +
-                                                        (24.f * kSsPi) * sinf(glow_r) / (glow_r * glow_r * glow_r));
-        float target = ss.sun_disk_intensity * kSsPi;
-        float max_glow = 0.5f * target;
-        if (glow_integral > max_glow) {
-          glow_scale *= max_glow / glow_integral;
-          target -= max_glow;
-        } else
-          target -= glow_integral;
-        float area = 2 * kSsPi * (1 - cosf(disk_r));
-        float target_intensity = target / area;
-        float actual_intensity = ss.sun_disk_intensity * 100.0f * (1.0f * area) / area;
-        disk_scale = (target_intensity == 0.0f) ? 0.0f : target_intensity / actual_intensity;
-      }
-      float f = (1.0f - sun_angle / sun_radius) * 10.0f;
-      f = powf(f / 10.0f, 3.0f) * 2.0f * ss.sun_glow_intensity * glow_scale +
-          smoothstepf(8.5f, 9.5f + (haze / 50.0f), f) * 100.0f * ss.sun_disk_intensity * disk_scale;
+    if (sun_angle < p.sun_radius) {
+      float f = (1.0f - sun_angle / p.sun_radius) * 10.0f;
+      f = powf(f / 10.0f, 3.0f) * 2.0f * ss.sun_glow_intensity * p.glow_scale +
+          smoothstepf(8.5f, 9.5f + (haze / 50.0f), f) * 100.0f * ss.sun_disk_intensity * p.disk_scale;
       tint += sun_color * f;
     }
   }
   float3 out = tint * rgb_scale;
   if (downness <= 0.0f) {
-    const float3 irrad = ground_irrad;  // calc_irrad :245-262, hoisted: see sky_ground_irradiance
-    float3 down = f3(ss.ground_color) * ((irrad + sun_color * sun.z) * rgb_scale);
+    float3 down = f3(ss.ground_color) * ((f3(p.ground_irrad) + sun_color * sun.z) * rgb_scale);
     if (factor < 1) down *= factor;
     float blur = ss.horizon_blur / 10.0f;
     if (blur > 0.0f) {
@@ -476,7 +540,7 @@ ADEV float3 sample_lights(const ShadeEnv& se, PathRegs& p, float3 pos, float3 no
     if (sk.in_use == 1) {
       ls.d = uniform_sample_sphere(u);
       ls.pdf = kInv4Pi;
-      radiance = sun_and_sky(sk, ls.d, f3(se.fp->sky_ground_irrad));
+      radiance = sun_and_sky(sk, se.fp->sky, ls.d);
     } else if (pc.hasEnvMap == 1) {
       radiance = env_sample(se.env, u, ls.d, ls.pdf);
     } else {
@@ -1370,7 +1434,7 @@ ADEV void shade_miss(const ShadeEnv& se, PathRegs& p) {
   const AsunaSunSky& sk = se.fp->sunsky;
   p.stop = true;
   float3 d = p.ray_d, env;
-  if (sk.in_use == 1) env = sun_and_sky(sk, d, f3(se.fp->sky_ground_irrad));
+  if (sk.in_use == 1) env = sun_and_sky(sk, se.fp->sky, d);
   else if (pc.hasEnvMap == 1) env = env_eval(se.env, d);
   else env = f3(pc.bgColor);
   float mis = 1.0f;
