@@ -44,3 +44,62 @@ def rays_toward(origin, targets):
     rays = np.zeros((len(d), 8), np.float32)
     rays[:, :3], rays[:, 4:7], rays[:, 3], rays[:, 7] = origin, d, 1e-5, 1e10
     return rays
+
+
+# ---- closed forms of the rendering equation (independent of any restatement of the reference) ----------------------
+def rect_form_factor_center(a, b, h):
+    """Form factor from a differential element to a parallel (2a x 2b) rectangle centred at height h above it
+    (four corner configurations; e.g. Howell, A Catalog of Radiation Heat Transfer Configuration Factors, B-3)."""
+    import math
+
+    def corner(a, b, h):
+        A, B = math.sqrt(a * a + h * h), math.sqrt(b * b + h * h)
+        return (a / A * math.atan(b / A) + b / B * math.atan(a / B)) / (2 * math.pi)
+    return 4 * corner(a, b, h)
+
+
+DIRECT_ALBEDO, DIRECT_RADIANCE, DIRECT_HEIGHT = (0.6, 0.5, 0.4), (3.0, 2.0, 1.0), 1.5
+
+
+def direct_light_scene(kind, spp):
+    """A large lambertian plane lit by one light 1.5 above the origin, seen through a 0.5 degree camera aimed at the
+    origin, path depth 2: every pixel estimates the direct illumination of (almost) the same point.
+    kind 'rect': a 2 x 1 one-sided rectangle facing down -> Lo = albedo * L * F (form factor above);
+    kind 'point': Lo = albedo / pi * I / h^2 (the reference divides by dist + EPS and dist^2 + EPS, A.3-12: -0.2 %)."""
+    from asuna_b200 import host, scenes, structs as S
+    sc = host.Scene()
+    sc.set_camera("perspective", 8, 8, fov=0.5)
+    sc.state["spp"], sc.state["maxPathDepth"] = spp, 2
+    sc.add_material("m", scenes.mat(S.MAT_LAMBERTIAN, diffuse=DIRECT_ALBEDO))
+    sc.add_mesh("plane", *scenes.grid_plane(2, 50.0, 0.0))
+    sc.add_instance("plane", "m")
+    h = DIRECT_HEIGHT
+    if kind == "rect":
+        sc.add_light(scenes.rect_light((-1, h, -0.5), (1, h, -0.5), (-1, h, 0.5), DIRECT_RADIANCE))
+    else:
+        sc.add_light(scenes.point_light((0, h, 0), DIRECT_RADIANCE))
+    sc.shots.append(host.Shot((3.0, 2.0, 0.0), (0, 0, 0), (0, 1, 0)))
+    return sc
+
+
+def direct_light_expected(kind):
+    import math
+    alb, L = np.asarray(DIRECT_ALBEDO), np.asarray(DIRECT_RADIANCE)
+    if kind == "rect":
+        return alb * L * rect_form_factor_center(1.0, 0.5, DIRECT_HEIGHT)
+    return alb / math.pi * L / DIRECT_HEIGHT ** 2
+
+
+def mirror_plane_scene():
+    """A mirror plane (reflectance 0.9, 0.8, 0.7) under a constant background (0.5, 0.25, 0.125): every pixel is the
+    product, exactly (delta reflection, no MIS on specular paths, raytrace.default.rmiss:24-55)."""
+    from asuna_b200 import host, scenes, structs as S
+    sc = host.Scene()
+    sc.set_camera("perspective", 16, 16, fov=30.0)
+    sc.state["spp"], sc.state["maxPathDepth"] = 4, 3
+    sc.state["bgColor"] = (0.5, 0.25, 0.125)
+    sc.add_material("m", scenes.mat(S.MAT_MIRROR, diffuse=(0.9, 0.8, 0.7)))
+    sc.add_mesh("plane", *scenes.grid_plane(2, 50.0, 0.0))
+    sc.add_instance("plane", "m")
+    sc.shots.append(host.Shot((3.0, 2.0, 0.0), (0, 0, 0), (0, 1, 0)))
+    return sc

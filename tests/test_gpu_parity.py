@@ -147,6 +147,26 @@ def test_closed_forms_on_gpu(gpu_ctx):
     assert np.allclose(img[16, 16, :3], [10, 10, 4], atol=1e-4)
 
 
+@pytest.mark.parametrize("kind,tol", [("rect", 0.003), ("point", 0.004)])
+def test_direct_lighting_matches_the_rendering_equation_on_gpu(gpu_ctx, kind, tol):
+    """The CUDA path against closed forms of the rendering equation (helpers.direct_light_scene): analytic form factor
+    of a rectangular emitter, inverse-square law of a point light."""
+    from helpers import direct_light_expected, direct_light_scene
+    sc = direct_light_scene(kind, 8192)
+    sc.upload(gpu_ctx)
+    img = sc.render_shot(gpu_ctx, 0)[0]
+    got = img[..., :3].reshape(-1, 3).mean(0)
+    assert np.abs(got / direct_light_expected(kind) - 1.0).max() <= tol, got / direct_light_expected(kind)
+
+
+def test_mirror_plane_reflects_the_background_on_gpu(gpu_ctx):
+    from helpers import mirror_plane_scene
+    sc = mirror_plane_scene()
+    sc.upload(gpu_ctx)
+    img = sc.render_shot(gpu_ctx, 0)[0]
+    assert np.allclose(img[..., :3], [0.45, 0.2, 0.0875], atol=1e-6)
+
+
 def test_pinned_read_back_equals_pageable(gpu_ctx):
     """asuna_host_alloc hands out page-locked buffers for asuna_read_channel (≙ the mapped staging buffer of
     tracer.cpp:317-336); the image must be the one a plain host pointer receives."""
