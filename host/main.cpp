@@ -1,6 +1,6 @@
 // asuna_b200 -- headless command line of the B200 path tracer.  Flags of the reference (src/main.cpp:18-24):
 //   --offline  --gpu_id N  --output_scanline  --out PATH  --scene PATH  --spp N
-// plus  --gpus N (1/2/4/8, frames of a shot split over the GPUs), --output_f32, --dump-scene FILE, --report FILE.
+// plus  --gpus N (1/2/4/8, frames of a shot split over the GPUs; --split shots gives every GPU whole shots instead), --output_f32, --dump-scene FILE, --report FILE.
 // There is no window system on a B200 box: the online (GLFW) mode of the reference does not exist here and
 // rendering is always the offline path.  `--spp` is accepted and ignored exactly like the reference does
 // (Scene::setSpp drops its argument, src/scene/scene.cpp:373): spp comes from the scene file / the shot.
@@ -16,7 +16,7 @@ using namespace asuna_host;
 
 static void usage() {
   fprintf(stderr,
-          "usage: asuna_b200 --scene scene.json [--out PREFIX] [--offline] [--gpu_id N] [--gpus N] [--output_scanline]\n"
+          "usage: asuna_b200 --scene scene.json [--out PREFIX] [--offline] [--gpu_id N] [--gpus N] [--split frames|shots] [--output_scanline]\n"
           "                  [--output_f32] [--spp N (ignored, as in the reference)] [--dump-scene FILE] [--report FILE]\n");
 }
 
@@ -38,6 +38,14 @@ int main(int argc, char** argv) {
     if (a == "--offline") offline_given = true;
     else if (a == "--gpu_id") tis.gpu_id = atoi(value().c_str());
     else if (a == "--gpus") tis.n_gpus = atoi(value().c_str());
+    else if (a == "--split") {  // frames (default): frame ranges of each shot + NCCL reduce; shots: whole shots per GPU
+      std::string m = value();
+      if (m != "frames" && m != "shots") {
+        fprintf(stderr, "[x] --split takes frames or shots\n");
+        exit(1);
+      }
+      tis.split_shots = m == "shots";
+    }
     else if (a == "--output_scanline") tis.output_scanline = true;
     else if (a == "--output_f32") tis.output_f32 = true;
     else if (a == "--out") tis.outputname = value();

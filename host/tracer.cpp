@@ -83,7 +83,8 @@ void Tracer::init() {
     th.emplace_back([&, g] {
       try {
         ms[g] = m_scene.upload(m_ctx[g]);
-        check(m_ctx[g], asuna_set_partition(m_ctx[g], (uint32_t)g, (uint32_t)n), "asuna_set_partition");
+        if (!m_tis.split_shots)  // frame ranges of every shot; with --split shots each GPU renders whole shots
+          check(m_ctx[g], asuna_set_partition(m_ctx[g], (uint32_t)g, (uint32_t)n), "asuna_set_partition");
       } catch (const std::exception& e) {
         err[g] = e.what();
       }
@@ -92,7 +93,7 @@ void Tracer::init() {
   for (auto& e : err)
     if (!e.empty()) throw std::runtime_error(e);
   m_build_ms = ms[0];
-  if (n > 1) {
+  if (n > 1 && !m_tis.split_shots) {
     std::vector<ncclComm_t> comms(n);
     if (ncclCommInitAll(comms.data(), n, devs.data()) != ncclSuccess) throw std::runtime_error("ncclCommInitAll failed");
     for (auto c : comms) m_comms.push_back((void*)c);
@@ -102,6 +103,32 @@ void Tracer::init() {
 std::vector<ShotReport> Tracer::run() {
   std::vector<ShotReport> reports;
   const int n = (int)m_ctx.size();
+  if (n > 1 && m_tis.split_shots) {
+    // replicas: shot s goes to GPU s % n as a whole -- no communication; a group of n shots is queued on
+    // the n GPUs at once (asuna_render_frames is asynchronous), then read back and saved one after the other
+    for (size_t first = 0; first < m_scene.shots.size(); first += (size_t)n) {
+      const int cnt = (int)std::min<size_t>((size_t)n, m_scene.shots.size() - first);
+      double t0 = now_ms();
+      std::vector<int> tot(cnt, 0);
+      for (int g = 0; g < cnt; g++) {
+        tot[g] = m_scene.begin_shot(m_ctx[g], first + (size_t)g);
+        check(m_ctx[g], asuna_render_frames(m_ctx[g], (uint32_t)tot[g]), "asuna_render_frames");
+      }
+      for (int g = 0; g < cnt; g++) check(m_ctx[g], asuna_sync(m_ctx[g]), "asuna_sync");
+      double render_ms = now_ms() - t0;
+      for (int g = 0; g < cnt; g++) {
+        ShotReport rep;
+        rep.shot = (int)first + g, rep.spp = tot[g], rep.render_ms = render_ms / cnt;
+        double t1 = now_ms();
+        save_shot(rep.shot, g);
+        rep.save_ms = now_ms() - t1;
+        fprintf(stderr, "[info] shot %04d on GPU %d: %d spp, group of %d shots in %.1f ms, saved in %.1f ms\n", rep.shot,
+                m_tis.gpu_id + g, tot[g], cnt, render_ms, rep.save_ms);
+        reports.push_back(rep);
+      }
+    }
+    return reports;
+  }
   for (size_t shot = 0; shot < m_scene.shots.size(); shot++) {
     ShotReport rep;
     rep.shot = (int)shot;
@@ -140,31 +167,31 @@ std::vector<ShotReport> Tracer::run() {
 }
 
 // callSavingImage, src/tracer/tracer.cpp:266-291
-void Tracer::save_shot(int shot_id) {
+void Tracer::save_shot(int shot_id, int gpu) {
   char name[4096];
   const OutputOptions& o = m_scene.output;
   if (!o.render_result) return;
   if (o.hdr) {
     snprintf(name, sizeof name, "%s_shot_%04d.exr", m_tis.outputname.c_str(), shot_id);
-    save_buffer(name, 0);
+    save_buffer(name, 0, gpu);
   } else {
     snprintf(name, sizeof name, "%s_shot_%04d.png", m_tis.outputname.c_str(), shot_id);
-    save_buffer(name, -1);
+    save_buffer(name, -1, gpu);
   }
   for (uint32_t cid = 0; cid < m_scene.state.nMultiChannel; cid++) {
     bool ldr = cid < o.channel_ldr.size() && o.channel_ldr[cid];
     snprintf(name, sizeof name, "%s_shot_%04d_channel_%04d.%s", m_tis.outputname.c_str(), shot_id, (int)cid, ldr ? "png" : "exr");
-    save_buffer(name, (int)cid + 1);
+    save_buffer(name, (int)cid + 1, gpu);
   }
 }
 
 // saveBufferToImage, src/tracer/tracer.cpp:347-395
-void Tracer::save_buffer(const std::string& path_in, int channel_id) {
+void Tracer::save_buffer(const std::string& path_in, int channel_id, int gpu) {
   std::string path = path_in;
   if (path.empty() || path[0] != '/') path = exe_dir() + path;  // relative paths are taken from the executable's directory
   const int w = m_scene.camera.width, h = m_scene.camera.height;
   std::vector<float> data((size_t)w * h * 4);
-  check(m_ctx[0], asuna_read_channel(m_ctx[0], channel_id < 0 ? 0 : channel_id, data.data()), "asuna_read_channel");
+  check(m_ctx[gpu], asuna_read_channel(m_ctx[gpu], channel_id < 0 ? 0 : channel_id, data.data()), "asuna_read_channel");
   if (channel_id < 0) {  // the post-processed colour: tone mapping of the raw radiance (no denoiser on this path)
     std::vector<float> ldr(data.size());
     tonemap(m_scene.output.tone_mapping, w * h, data.data(), ldr.data());

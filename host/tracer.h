@@ -14,6 +14,7 @@ struct TracerSettings {  // TracerInitSettings, src/tracer/tracer.h + src/main.c
   std::string scenefile, outputname;
   int gpu_id = 0;
   int n_gpus = 1;
+  bool split_shots = false;   // extension: with n_gpus > 1 give every GPU whole shots (replicas, no reduce) instead of frame ranges
   bool offline = true;
   bool output_scanline = false;
   bool output_f32 = false;    // extension: also write <image>.npy with the full float32 RGBA plane
@@ -38,8 +39,8 @@ class Tracer {
   float build_ms() const { return m_build_ms; }
 
  private:
-  void save_shot(int shot_id);
-  void save_buffer(const std::string& outputpath, int channel_id);
+  void save_shot(int shot_id, int gpu = 0);
+  void save_buffer(const std::string& outputpath, int channel_id, int gpu = 0);
   TracerSettings m_tis;
   Scene m_scene;
   std::vector<asuna_ctx*> m_ctx;

@@ -87,3 +87,21 @@ def test_cli_two_gpus_match_one(tmp_path):
     a, b = np.load(str(tmp_path / "one_shot_0000.exr.npy")), np.load(str(tmp_path / "two_shot_0000.exr.npy"))
     assert np.allclose(a[..., :3], b[..., :3], rtol=3e-5, atol=3e-6)  # same samples, other summation order
     assert np.array_equal(np.load(str(tmp_path / "one_shot_0000_channel_0000.exr.npy")), np.load(str(tmp_path / "two_shot_0000_channel_0000.exr.npy")))
+
+
+def test_cli_two_gpus_split_by_shots(tmp_path):
+    """--split shots (replicas): every GPU renders whole shots, nothing is exchanged, so each image is
+    the one a single GPU writes, bit for bit."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sc = scenes.cornell(48, 40, spp=4, depth=4)
+    scenes.orbit_shots(sc, 3, (0.5, 0.5, 0.5), 2.2, 0.5)
+    path = gen_scenes.write_scene(sc, str(tmp_path), "c")
+    _run(["--offline", "--scene", path, "--out", str(tmp_path / "one"), "--output_f32"])
+    _run(["--offline", "--scene", path, "--out", str(tmp_path / "two"), "--output_f32", "--gpus", "2", "--split", "shots"])
+    for shot in range(3):
+        for suffix in (".exr.npy", "_channel_0000.exr.npy"):
+            a = np.load(str(tmp_path / f"one_shot_{shot:04d}{suffix}"))
+            b = np.load(str(tmp_path / f"two_shot_{shot:04d}{suffix}"))
+            assert np.array_equal(a, b, equal_nan=True), (shot, suffix)
