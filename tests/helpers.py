@@ -59,13 +59,15 @@ def rect_form_factor_center(a, b, h):
 
 
 DIRECT_ALBEDO, DIRECT_RADIANCE, DIRECT_HEIGHT = (0.6, 0.5, 0.4), (3.0, 2.0, 1.0), 1.5
+DIRECT_DIRECTION = (0.3, 1.0, 0.2)  # towards the distant light
 
 
 def direct_light_scene(kind, spp):
     """A large lambertian plane lit by one light 1.5 above the origin, seen through a 0.5 degree camera aimed at the
     origin, path depth 2: every pixel estimates the direct illumination of (almost) the same point.
     kind 'rect': a 2 x 1 one-sided rectangle facing down -> Lo = albedo * L * F (form factor above);
-    kind 'point': Lo = albedo / pi * I / h^2 (the reference divides by dist + EPS and dist^2 + EPS, A.3-12: -0.2 %)."""
+    kind 'point': Lo = albedo / pi * I / h^2 (the reference divides by dist + EPS and dist^2 + EPS, A.3-12: -0.2 %);
+    kind 'distant': Lo = albedo / pi * L * cos(theta)."""
     from asuna_b200 import host, scenes, structs as S
     sc = host.Scene()
     sc.set_camera("perspective", 8, 8, fov=0.5)
@@ -76,6 +78,8 @@ def direct_light_scene(kind, spp):
     h = DIRECT_HEIGHT
     if kind == "rect":
         sc.add_light(scenes.rect_light((-1, h, -0.5), (1, h, -0.5), (-1, h, 0.5), DIRECT_RADIANCE))
+    elif kind == "distant":
+        sc.add_light(scenes.distant_light(DIRECT_DIRECTION, DIRECT_RADIANCE))
     else:
         sc.add_light(scenes.point_light((0, h, 0), DIRECT_RADIANCE))
     sc.shots.append(host.Shot((3.0, 2.0, 0.0), (0, 0, 0), (0, 1, 0)))
@@ -87,6 +91,9 @@ def direct_light_expected(kind):
     alb, L = np.asarray(DIRECT_ALBEDO), np.asarray(DIRECT_RADIANCE)
     if kind == "rect":
         return alb * L * rect_form_factor_center(1.0, 0.5, DIRECT_HEIGHT)
+    if kind == "distant":  # irradiance L cos(theta) of a directional source
+        d = np.asarray(DIRECT_DIRECTION, np.float64)
+        return alb / math.pi * L * (d[1] / np.linalg.norm(d))
     return alb / math.pi * L / DIRECT_HEIGHT ** 2
 
 

@@ -147,7 +147,7 @@ def test_closed_forms_on_gpu(gpu_ctx):
     assert np.allclose(img[16, 16, :3], [10, 10, 4], atol=1e-4)
 
 
-@pytest.mark.parametrize("kind,tol", [("rect", 0.003), ("point", 0.004)])
+@pytest.mark.parametrize("kind,tol", [("rect", 0.003), ("point", 0.004), ("distant", 0.0012)])  # delta lights: the reference divides by pdf + EPS = 1.001
 def test_direct_lighting_matches_the_rendering_equation_on_gpu(gpu_ctx, kind, tol):
     """The CUDA path against closed forms of the rendering equation (helpers.direct_light_scene): analytic form factor
     of a rectangular emitter, inverse-square law of a point light."""
