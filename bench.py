@@ -123,11 +123,15 @@ def ncu_traffic():
 
 # ----------------------------------------------------------------------------- CPU arm
 def cpu_run(args, steps, warmup, budget_s=None):
-    """Times the CPU oracle (a port of the reference shaders; the reference itself needs a Vulkan RT device
-    and cannot run here) on the same workload.  A step is one 1-spp 1080p frame."""
-    from oracle.binding import OracleContext
+    """Times the reference's per-pixel program on the host cores, same workload; a step is one 1-spp frame.
+    kind "reference": oracle/_ref/libref.so -- the reference's own GLSL (rgen, rmiss, all rchit, utils) compiled as
+    C++ against the GLM vendored in its tree (oracle/refbuild/build_ref.py), with the oracle's SAH BVH2 answering
+    traceRayEXT (the reference leaves that to the Vulkan driver and cannot run without an RT device).
+    kind "port": oracle/liboracle.so, the hand restatement, when libref.so was not built."""
+    from oracle import binding
     sc = build_scene(args)
-    ctx = OracleContext()
+    kind = "reference" if os.path.exists(binding.REF_LIB) else "port"
+    ctx = binding.RefContext() if kind == "reference" else binding.OracleContext()
     cores = os.cpu_count() or 1
     sc.upload(ctx)
     sc.begin_shot(ctx, 0)
@@ -144,8 +148,9 @@ def cpu_run(args, steps, warmup, budget_s=None):
     samples = done * args.width * args.height
     st = ctx.stats()
     ctx.close()
-    return {"value": samples / dt, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{done} x 1-spp {args.width}x{args.height} frames of the same scene ({dt:.1f} s, BVH build excluded)",
+    what = "reference GLSL compiled as C++ (GLM) + oracle BVH2" if kind == "reference" else "CPU oracle port"
+    return {"value": samples / dt, "unit": UNIT, "cores": cores, "kind": kind,
+            "sample": f"{done} x 1-spp {args.width}x{args.height} frames of the same scene ({dt:.1f} s, BVH build excluded); {what}",
             "ms_per_step": 1e3 * dt / max(done, 1), "steps": done,
             "mrays_per_s": (st["closest_rays"] + st["shadow_rays"]) / max(st["total_ms"], 1e-9) / 1e3}
 
@@ -161,7 +166,7 @@ def run_reference_arm(args):
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "mrays_per_s": r["mrays_per_s"], "gpu_launches": 0,
-            "note": "CPU oracle port of the reference shaders on all host threads; one step = one 1-spp frame"}
+            "note": "the reference's per-pixel program on all host threads (see cpu_baseline.kind / sample); one step = one 1-spp frame"}
     print(json.dumps(line))
     return 0
 

@@ -34,6 +34,10 @@
 
 #include "bvh.h"
 #include "shading.h"
+// ref_bridge.h: plain-C structs shared with oracle/_ref/libref.so (oracle/refbuild/build_ref.py), which is this
+// file compiled with -DASUNA_REF_SHADERS: same scene store, BVH and C ABI, but the per-pixel program is the
+// reference's own GLSL compiled as C++ instead of the restatement below.
+#include "refbuild/ref_bridge.h"
 
 using namespace orc;
 
@@ -1684,6 +1688,10 @@ int oracle_set_state(oracle_ctx* c, const AsunaState* s) {
 int oracle_reset_frame(oracle_ctx* c) {
   c->pc.curFrame = -1;
   c->have_accum = false;
+#ifdef ASUNA_REF_SHADERS
+  std::fill(c->images[0].begin(), c->images[0].end(), 0.0f);
+  std::fill(c->images[8].begin(), c->images[8].end(), 0.0f);
+#endif
   return 0;
 }
 int oracle_set_partition(oracle_ctx* c, uint32_t rank, uint32_t world) {
@@ -1691,6 +1699,48 @@ int oracle_set_partition(oracle_ctx* c, uint32_t rank, uint32_t world) {
   c->rank = rank, c->world = world;
   return 0;
 }
+#ifdef ASUNA_REF_SHADERS
+// traceRayEXT's geometric query, answered by the oracle BVH for the generated reference shaders.
+static int ref_trace_cb(void* ctx, const float o[3], const float d[3], float tmin, float tmax, int any, RefHit* out) {
+  oracle_ctx* c = static_cast<oracle_ctx*>(ctx);
+  Hit h;
+  if (any)
+    c->n_shadow.fetch_add(1, std::memory_order_relaxed);
+  else
+    c->n_closest.fetch_add(1, std::memory_order_relaxed);
+  if (!c->trace(vec3(o), vec3(d), tmin, tmax, any != 0, h)) return 0;
+  out->t = h.t, out->b1 = h.b1, out->b2 = h.b2, out->inst = h.inst, out->prim = h.prim;
+  std::memcpy(out->o2w, c->instances[h.inst].o2w, sizeof out->o2w);
+  std::memcpy(out->w2o, c->instances[h.inst].w2o, sizeof out->w2o);
+  return 1;
+}
+static void ref_bind(oracle_ctx* c) {
+  static std::vector<RefTex> tex;
+  static std::vector<RefInst> inst;
+  tex.resize(c->textures.size());
+  for (size_t i = 0; i < tex.size(); i++) tex[i] = RefTex{c->textures[i].rgba.data(), (int32_t)c->textures[i].w, (int32_t)c->textures[i].h};
+  inst.resize(c->instances.size());
+  for (size_t i = 0; i < inst.size(); i++) {
+    const Instance& in = c->instances[i];
+    const Mesh& m = c->meshes[in.mesh];
+    const AsunaMaterial* mat = in.light >= 0 ? nullptr : &c->materials[in.material];
+    inst[i] = RefInst{m.v.data(), m.idx.data(), mat, in.light, mat ? mat->type : (uint32_t)ASUNA_MAT_LAMBERTIAN};
+  }
+  RefBind b{};
+  b.ctx = c, b.trace = ref_trace_cb;
+  b.camera = &c->cam, b.sunsky = &c->sunsky, b.pc = &c->pc, b.lights = c->lights.data();
+  b.n_textures = (uint32_t)tex.size(), b.textures = tex.data();
+  for (int i = 0; i < 3; i++) b.env[i] = RefTex{c->env[i].rgba.data(), (int32_t)c->env[i].w, (int32_t)c->env[i].h};
+  b.n_instances = (uint32_t)inst.size(), b.instances = inst.data();
+  for (int i = 0; i < ASUNA_NUM_OUTPUT_IMAGES; i++) b.images[i] = c->images[i].data();
+  b.width = c->W, b.height = c->H;
+  refglsl_bind(&b);
+}
+int oracle_is_reference_glsl(void) { return 1; }
+#else
+int oracle_is_reference_glsl(void) { return 0; }
+#endif
+
 int oracle_render_frames(oracle_ctx* c, uint32_t n) {
   if (!c->built || c->W == 0) {
     c->err = "render before build_accel/set_film";
@@ -1703,9 +1753,19 @@ int oracle_render_frames(oracle_ctx* c, uint32_t n) {
     int cf = c->pc.curFrame;
     if ((uint32_t)cf % c->world != c->rank) continue;
     bool first = !c->have_accum;
+#ifdef ASUNA_REF_SHADERS
+    // rgen:155-178 decides replace-vs-accumulate on curFrame == 0; a partition whose first frame is not 0
+    // accumulates onto the planes zeroed by reset_frame, which is the same arithmetic as `first` below.
+    (void)first;
+    ref_bind(c);
+    parallel_for((int64_t)c->H, 2, nthreads, [&](int64_t y) {
+      for (uint32_t x = 0; x < c->W; x++) refglsl_render_pixel(x, (uint32_t)y);
+    });
+#else
     parallel_for((int64_t)c->H, 2, nthreads, [&](int64_t y) {
       for (uint32_t x = 0; x < c->W; x++) c->renderPixel(x, (uint32_t)y, cf, first);
     });
+#endif
     c->have_accum = true;
     c->stats.paths += (uint64_t)c->W * c->H;
   }
@@ -1799,6 +1859,56 @@ int oracle_trace_primary(oracle_ctx* c, uint32_t* ip, float* t) {
 }
 
 // ---- unit-test hooks: expose individual restated functions so tests can pin them ----
+// n independent closest-hit (inst/prim/b1/b2 given) or miss (inst = 0xFFFFFFFF) shader invocations on caller-made payloads.
+static int shade_probe_one(oracle_ctx* c, uint32_t inst, uint32_t prim, float b1, float b2, ShadeProbe* q) {
+  const bool is_hit = inst != 0xFFFFFFFFu;
+  if (is_hit && (inst >= c->instances.size() || 3 * (size_t)prim >= c->meshes[c->instances[inst].mesh].idx.size())) return ASUNA_E_INVALID;
+#ifdef ASUNA_REF_SHADERS
+  RefHit h{};
+  if (is_hit) {
+    h.b1 = b1, h.b2 = b2, h.inst = inst, h.prim = prim;
+    std::memcpy(h.o2w, c->instances[inst].o2w, sizeof h.o2w);
+    std::memcpy(h.w2o, c->instances[inst].w2o, sizeof h.w2o);
+  }
+  refglsl_shade_probe(is_hit ? &h : nullptr, q);
+#else
+  auto st = [](float* f, vec3 v) { f[0] = v.x, f[1] = v.y, f[2] = v.z; };
+  RayPayload p;
+  p.pRec.ray = Ray{vec3(q->ray_o), vec3(q->ray_d)};
+  p.pRec.radiance = vec3(q->radiance), p.pRec.throughput = vec3(q->throughput);
+  p.pRec.depth = (int)q->depth, p.pRec.seed = q->seed, p.pRec.stop = q->stop != 0;
+  p.bRec.d = vec3(q->brec_d), p.bRec.pdf = q->brec_pdf, p.bRec.flags = q->brec_flags;
+  p.dRec.skip = true;
+  p.dRec.radiance = vec3(0.0f);
+  p.dRec.dist = 0, p.dRec.ray = Ray{vec3(0.0f), vec3(0.0f)};
+  for (auto& ch : p.channel) ch = vec3(0.0f);
+  if (is_hit) {
+    Hit h;
+    h.b1 = b1, h.b2 = b2, h.inst = inst, h.prim = prim;
+    c->closestHit(p, h);
+  } else {
+    c->miss(p);
+  }
+  st(q->ray_o, p.pRec.ray.o), st(q->ray_d, p.pRec.ray.d), st(q->radiance, p.pRec.radiance), st(q->throughput, p.pRec.throughput);
+  q->depth = (uint32_t)p.pRec.depth, q->seed = p.pRec.seed, q->stop = p.pRec.stop ? 1u : 0u;
+  st(q->brec_d, p.bRec.d), q->brec_pdf = p.bRec.pdf, q->brec_flags = p.bRec.flags;
+  st(q->drec_radiance, p.dRec.radiance), q->drec_dist = p.dRec.dist;
+  st(q->drec_o, p.dRec.ray.o), st(q->drec_d, p.dRec.ray.d), q->drec_skip = p.dRec.skip ? 1u : 0u;
+  for (int i = 0; i < 8; i++) st(q->channel[i], p.channel[i]);
+#endif
+  return 0;
+}
+int oracle_shade_probes(oracle_ctx* c, uint32_t n, const uint32_t* inst, const uint32_t* prim, const float* b1,
+                        const float* b2, ShadeProbe* q) {
+#ifdef ASUNA_REF_SHADERS
+  ref_bind(c);
+#endif
+  for (uint32_t i = 0; i < n; i++) {
+    int rc = shade_probe_one(c, inst[i], prim[i], b1[i], b2[i], q + i);
+    if (rc) return rc;
+  }
+  return 0;
+}
 uint32_t oracle_xxhash32(uint32_t x, uint32_t y, uint32_t z) { return xxhash32Seed(x, y, z); }
 uint32_t oracle_pcg(uint32_t* state) { return pcg(*state); }
 float oracle_rand(uint32_t* state) { return rand1(*state); }
@@ -1809,6 +1919,43 @@ void oracle_sun_and_sky(const AsunaSunSky* ss, const float d[3], float out[3]) {
 void oracle_offset_position(const float p[3], const float n[3], float out[3]) {
   vec3 r = offsetPositionAlongNormal(vec3(p), vec3(n));
   out[0] = r.x, out[1] = r.y, out[2] = r.z;
+}
+void oracle_basis(const float n[3], float f[3], float r[3]) {
+  vec3 F, R;
+  basis(vec3(n), F, R);
+  f[0] = F.x, f[1] = F.y, f[2] = F.z, r[0] = R.x, r[1] = R.y, r[2] = R.z;
+}
+void oracle_concentric_disk(const float u[2], float out[2]) {
+  vec2 r = concentricSampleDisk(vec2{u[0], u[1]});
+  out[0] = r.x, out[1] = r.y;
+}
+void oracle_cosine_hemisphere(const float u[2], float out[3]) {
+  vec3 r = cosineSampleHemisphere(vec2{u[0], u[1]});
+  out[0] = r.x, out[1] = r.y, out[2] = r.z;
+}
+void oracle_uniform_sphere(const float u[2], float out[3]) {
+  vec3 r = uniformSampleSphere(vec2{u[0], u[1]});
+  out[0] = r.x, out[1] = r.y, out[2] = r.z;
+}
+float oracle_power_heuristic(float a, float b) { return powerHeuristic(a, b); }
+// out = radiance(3) d(3) n(3) dist pdf flags, like refglsl_sample_one_light
+void oracle_sample_one_light(const AsunaLight* light, const float r[2], const float pos[3], float out[12]) {
+  oracle_ctx c;
+  LightSamplingRecord rec;
+  vec3 L = c.sampleOneLight(vec2{r[0], r[1]}, *light, vec3(pos), rec);
+  out[0] = L.x, out[1] = L.y, out[2] = L.z, out[3] = rec.d.x, out[4] = rec.d.y, out[5] = rec.d.z;
+  out[6] = rec.n.x, out[7] = rec.n.y, out[8] = rec.n.z, out[9] = rec.dist, out[10] = rec.pdf, out[11] = (float)rec.flags;
+}
+// env-map sampling / lookup through the context's tables (set_envmap, set_camera for envTransform, set_state)
+void oracle_envmap_sample(oracle_ctx* c, const float r[2], float out[7]) {
+  vec3 L;
+  float pdf;
+  vec3 col = c->sampleEnvmap(vec2{r[0], r[1]}, L, pdf);
+  out[0] = col.x, out[1] = col.y, out[2] = col.z, out[3] = L.x, out[4] = L.y, out[5] = L.z, out[6] = pdf;
+}
+void oracle_envmap_eval_pdf(oracle_ctx* c, const float d[3], float out[4]) {
+  vec3 col = c->evalEnvmap(vec3(d));
+  out[0] = col.x, out[1] = col.y, out[2] = col.z, out[3] = c->pdfEnvmap(vec3(d));
 }
 void oracle_texture_bilinear(const float* rgba, uint32_t w, uint32_t h, float u, float v, float out[4]) {
   Texture t;

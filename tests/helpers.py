@@ -110,3 +110,94 @@ def mirror_plane_scene():
     sc.add_instance("plane", "m")
     sc.shots.append(host.Shot((3.0, 2.0, 0.0), (0, 0, 0), (0, 1, 0)))
     return sc
+
+
+# ----------------------------------------------------------------------------- shade probes (oracle vs oracle/_ref)
+import ctypes as _C  # noqa: E402
+
+# ShadeProbe of oracle/refbuild/ref_bridge.h
+PROBE = np.dtype([("ray_o", "f4", 3), ("ray_d", "f4", 3), ("radiance", "f4", 3), ("throughput", "f4", 3),
+                  ("depth", "u4"), ("seed", "u4"), ("stop", "u4"), ("brec_d", "f4", 3), ("brec_pdf", "f4"),
+                  ("brec_flags", "u4"), ("drec_radiance", "f4", 3), ("drec_dist", "f4"), ("drec_o", "f4", 3),
+                  ("drec_d", "f4", 3), ("drec_skip", "u4"), ("channel", "f4", (8, 3))])
+MISS = 0xFFFFFFFF
+
+
+def random_probes(rng, n, ntri, inst):
+    """n random shader invocations on instance `inst` (MISS = the miss shader): random triangle, barycentrics,
+    incoming direction (both sides of the surface), RNG state, depth, throughput and previous-bounce record."""
+    q = np.zeros(n, PROBE)
+    d = rng.randn(n, 3).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    q["ray_d"], q["ray_o"] = d, rng.rand(n, 3)
+    q["throughput"], q["radiance"] = rng.rand(n, 3), rng.rand(n, 3) * 0.1
+    q["depth"] = rng.randint(1, 4, n)
+    q["seed"] = rng.randint(0, 2 ** 32, n, dtype=np.uint64).astype(np.uint32)
+    q["brec_pdf"] = rng.rand(n) * 3
+    q["brec_flags"] = rng.choice([0, 1, 4, 16, 32], n)
+    b1 = rng.rand(n).astype(np.float32)
+    b2 = ((1 - b1) * rng.rand(n)).astype(np.float32)
+    return (np.full(n, inst, np.uint32), rng.randint(0, max(ntri, 1), n).astype(np.uint32), b1, b2, q)
+
+
+def run_probes(ctx, inst, prim, b1, b2, probes):
+    q = probes.copy()
+    p = lambda a: a.ctypes.data_as(_C.c_void_p)
+    ctx._call("shade_probes", _C.c_uint32(len(q)), p(inst), p(prim), p(b1), p(b2), p(q))
+    return q
+
+
+def probe_mismatch(A, B, tol=2e-4):
+    """Compares two probe result arrays.  Integer fields (RNG state after the shader = number of draws consumed,
+    depth, stop, sampled-lobe flags, shadow-ray skip) must be identical; float fields are compared as vectors,
+    |a - b| <= tol * max(1, |b|).  Returns {field: fraction of probes outside}."""
+    out = {}
+    for f in PROBE.names:
+        a, b = A[f], B[f]
+        if a.dtype.kind == "u":
+            bad = a != b
+        else:
+            a, b = a.reshape(len(a), -1).astype(np.float64), b.reshape(len(b), -1).astype(np.float64)
+            fa, fb = np.isfinite(a).all(axis=1), np.isfinite(b).all(axis=1)
+            with np.errstate(invalid="ignore"):
+                d = np.linalg.norm(np.where(np.isfinite(a - b), a - b, 0), axis=1)
+                scale = np.maximum(1.0, np.linalg.norm(np.where(np.isfinite(b), b, 0), axis=1))
+            bad = (fa != fb) | (fa & fb & (d > tol * scale))
+        if bad.any():
+            out[f] = float(bad.mean())
+    return out
+
+
+def random_material(rng, mtype, texture_ids):
+    """A random but valid GpuMaterial of the given type (parameter ranges of SURVEY.md 8d)."""
+    from asuna_b200 import structs as S
+    m = S.default_material()
+    m["type"] = mtype
+    m["diffuse"] = rng.uniform(0.05, 0.9, 3)
+    m["rhoSpec"] = rng.uniform(0.05, 0.9, 3)
+    m["anisoAlpha"] = rng.uniform(0.02, 0.9, 2)
+    m["ior"] = rng.uniform(1.05, 2.4)
+    m["roughness"] = rng.uniform(0.02, 0.95)
+    m["metalness"] = rng.uniform(0, 1)
+    for k in ("subsurface", "specularTint", "anisotropic", "sheen", "sheenTint", "clearcoat", "clearcoatGloss"):
+        m[k] = rng.uniform(0, 1)
+    m["specular"] = rng.uniform(0, 1)
+    m["radiance"] = rng.uniform(0.1, 4.0, 3)
+    m["radianceFactor"] = rng.uniform(0.5, 5.0, 3)
+    pick = lambda: int(rng.choice(texture_ids)) if (len(texture_ids) and rng.rand() < 0.5) else -1
+    for k in ("diffuseTextureId", "roughnessTextureId", "metalnessTextureId", "radianceTextureId", "normalTextureId",
+              "tangentTextureId", "opacityTextureId"):
+        m[k] = pick()
+    if mtype == S.MAT_PHONG:
+        m["specular"] = rng.uniform(2, 200)  # shininess
+    if mtype in (S.MAT_PLASTIC, S.MAT_ROUGH_PLASTIC):
+        m["radiance"][0] = rng.uniform(0.3, 0.9)  # fdrInt
+    # constant opacity (= pass-through probability) is aliased onto specular (pbr), metalness (kang18), rhoSpec.x (disney)
+    opacity = rng.uniform(0, 0.5) if rng.rand() < 0.5 else 0.0
+    if mtype == S.MAT_PBR:
+        m["specular"] = opacity
+    elif mtype == S.MAT_KANG18:
+        m["metalness"] = opacity
+    elif mtype == S.MAT_DISNEY:
+        m["rhoSpec"][0] = opacity
+    return m

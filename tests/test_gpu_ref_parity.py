@@ -1,0 +1,120 @@
+"""The CUDA path against the REFERENCE'S OWN SHADERS (oracle/_ref/libref.so: the reference GLSL compiled as C++,
+oracle/refbuild/build_ref.py -- prebuilt where /root/reference exists, it travels to the GPU box) and against the
+frames frozen from it (tests/golden/ref_frame_*.npz), with the BASELINE.json thresholds; then the same
+comparison at BASELINE size on the benched scene itself and on the other full-size configurations.
+Nothing here reads /root/reference at run time."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from asuna_b200 import metrics, scenes
+from test_gpu_parity import SCENES, silhouette_mask
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def ref_ctx():
+    """libref.so when it is there (kind 'reference'), else the hand restatement it is pinned to."""
+    from oracle import binding
+    ctx = binding.RefContext() if os.path.exists(binding.REF_LIB) else binding.OracleContext()
+    yield ctx
+    ctx.close()
+
+
+def check(sc, gpu, cpu, shot=0, spp=None, aov_tol=1e-4):
+    """BASELINE.json: primary ids >= 99.9 %, AOVs <= 1e-4 off silhouettes, radiance mean relative error <= 1 %,
+    FLIP <= 0.01 at equal spp."""
+    sc.upload(gpu), sc.upload(cpu)
+    sc.begin_shot(gpu, shot), sc.begin_shot(cpu, shot)
+    ig, tg = gpu.trace_primary()
+    ic, tc = cpu.trace_primary()
+    same = (ig == ic).all(axis=2)
+    assert same.mean() >= 0.999, f"primary ids agree on {same.mean():.5f}"
+    g, c = sc.render_shot(gpu, shot, spp), sc.render_shot(cpu, shot, spp)
+    interior = same & ~silhouette_mask(ic)
+    for k in range(1, len(g)):
+        d = np.abs(g[k][..., :3] - c[k][..., :3]).max(axis=2)
+        scale = max(1.0, float(np.abs(c[k][..., :3]).max()))
+        assert d[interior].max() <= aov_tol * scale, f"AOV {k} differs by {d[interior].max()}"
+    rel, fl = metrics.mean_relative_error(g[0], c[0]), metrics.flip(g[0], c[0])
+    assert rel <= 0.01 and fl <= 0.01, (rel, fl)
+    return rel, fl, float(same.mean())
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_gpu_vs_reference_glsl(name, gpu_ctx, ref_ctx):
+    check(SCENES[name](), gpu_ctx, ref_ctx)
+
+
+@pytest.mark.parametrize("name", ["cornell", "materials", "materials_env", "pbr_sunsky", "all_materials"])
+def test_gpu_vs_frozen_reference_glsl_frames(name, gpu_ctx):
+    from tools.make_ref_golden import FRAMES
+    g = np.load(os.path.join(GOLDEN, f"ref_frame_{name}.npz"))
+    sc = FRAMES[name]()
+    sc.upload(gpu_ctx)
+    sc.begin_shot(gpu_ctx, 0)
+    ids, _ = gpu_ctx.trace_primary()
+    same = (ids == g["ids"]).all(axis=2)
+    assert same.mean() >= 0.999
+    imgs = sc.render_shot(gpu_ctx, 0)
+    interior = same & ~silhouette_mask(g["ids"])
+    for k, aov in enumerate(g["aov"]):
+        d = np.abs(imgs[1 + k][..., :3] - aov[..., :3]).max(axis=2)
+        assert d[interior].max() <= 1e-4
+    assert metrics.mean_relative_error(imgs[0], g["radiance"]) <= 0.01 and metrics.flip(imgs[0], g["radiance"]) <= 0.01
+
+
+# ----------------------------------------------------------------------------- BASELINE size
+def test_full_size_benched_scene(gpu_ctx, ref_ctx):
+    """BASELINE configs[1] exactly as bench.py renders it: glass blob, 1920x1080, depth 8, subdiv 6 (114 816
+    triangles), 2048x1024 env map -- 2 spp against the reference shaders on the CPU (~2.1 M paths)."""
+    sc = scenes.glass_blob(1920, 1080, spp=2, depth=8, subdiv=6, env_size=(2048, 1024))
+    rel, fl, agree = check(sc, gpu_ctx, ref_ctx)
+    print(f"configs[1] 1080p: primary ids {agree:.5f}, mean rel {rel:.2e}, FLIP {fl:.2e}")
+
+
+def test_full_size_cornell_config0(gpu_ctx, ref_ctx):
+    """BASELINE configs[0]: Cornell box 512x512, depth 5 -- 8 of the 64 spp (equal spp on both sides)."""
+    check(scenes.cornell(512, 512, spp=8, depth=5), gpu_ctx, ref_ctx)
+
+
+def test_full_size_pbr_config2(gpu_ctx, ref_ctx):
+    """BASELINE configs[2]: two displaced spheres (655 872 triangles), 2048^2 albedo / roughness / metalness / normal
+    textures, sun & sky + point light, 1080p, depth 5 -- 1 spp (AOVs, ids) + 1 jittered frame."""
+    sc = scenes.pbr_spheres(1920, 1080, spp=2, depth=5, subdiv=7, tex_size=2048)
+    check(sc, gpu_ctx, ref_ctx)
+
+
+def test_million_triangle_ray_bench_config(gpu_ctx, ref_ctx):
+    """C4' (SURVEY.md 8d): the 1.31 M-triangle ray-bench mesh, primary ids + position AOV at a reduced film."""
+    sc = scenes.ray_bench(480, 270, subdiv=8, depth=4, spp=2)
+    check(sc, gpu_ctx, ref_ctx)
+
+
+def test_instanced_field_config3_reduced_film(gpu_ctx, ref_ctx):
+    """BASELINE configs[3]: 100 instances of a 327 k-triangle mesh (32.8 M instanced triangles, flattened on the GPU,
+    two-level on the CPU), mixed BSDFs, env + rect light -- full geometry, film reduced to 480x270, 2 spp."""
+    sc = scenes.instanced_field(480, 270, spp=2, depth=5, subdiv=7, grid=10)
+    check(sc, gpu_ctx, ref_ctx)
+
+
+def test_frame_batches_beyond_one_internal_batch(gpu_ctx, ref_ctx):
+    """24 frames of a 320x180 film = 3 internal batches of 8: the accumulation across batches against 24 reference
+    frames (rgen:171-178)."""
+    sc = scenes.cornell_materials(320, 180, spp=24, depth=5, env=True, lights="rect", textured=True)
+    check(sc, gpu_ctx, ref_ctx)
+
+
+def test_opacity_pass_through_scene(gpu_ctx, ref_ctx):
+    """pbr / kang18 / disney opacity: `rand < opacity` continues the ray through the surface with depth-- (the host
+    loop of render_batch re-launches until the queue drains); constant and textured opacity."""
+    sc = scenes.cornell_all_materials(160, 120, spp=8, depth=5, env=False, lights="all", textured=True)
+    for m in sc.materials:
+        if int(m["type"]) == 3:
+            m["specular"] = 0.35
+        elif int(m["type"]) == 1:
+            m["metalness"] = 0.35
+    check(sc, gpu_ctx, ref_ctx)
