@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "abi_sizes", "create", "destroy", "last_error", "set_film", "add_texture", "set_envmap", "add_mesh",
     "add_material", "set_lights", "add_instance", "build_accel", "set_camera", "set_sunsky", "set_state",
     "reset_frame", "render_frames", "set_partition", "sync", "read_channel", "export_partial",
-    "import_partial", "host_alloc", "host_free", "channel_device_ptr", "stream_handle", "set_counting", "get_stats", "reset_stats", "trace_primary", "trace_rays",
+    "import_partial", "host_alloc", "host_free", "channel_device_ptr", "stream_handle", "set_counting", "set_profiling", "get_stats", "reset_stats", "trace_primary", "trace_rays",
     "occlusion_rays", "accel_stats")
 
 
@@ -197,6 +197,9 @@ class Context:
 
     def set_counting(self, on):
         return self._call("set_counting", C.c_int(1 if on else 0))
+
+    def set_profiling(self, on):
+        return self._call("set_profiling", C.c_int(1 if on else 0))
 
     def stats(self):
         s = np.zeros((), S.Stats)

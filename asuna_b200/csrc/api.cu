@@ -101,6 +101,7 @@ struct asuna_ctx {
   uint32_t user_capacity = 0;
 
   AsunaStats stats{};
+  bool profiling = false;  // asuna_set_profiling: per-launch CUDA-event pairs feeding the *_ms statistics
   std::vector<TimedEvent> pending;
   std::vector<cudaEvent_t> event_pool;
 };
@@ -134,18 +135,29 @@ cudaEvent_t get_event(asuna_ctx* ctx) {
   cudaEventCreate(&e);
   return e;
 }
-struct ScopedTimer {  // brackets stream work with two events; elapsed time is collected at sync
+void collect_timers(asuna_ctx* ctx);
+// Brackets stream work with two events when profiling is on (asuna_set_profiling; off by default, so an
+// integration that renders frame after frame without ever asking for statistics records nothing).  Elapsed times
+// are collected wherever the stream is synchronised anyway; the backlog is bounded.
+struct ScopedTimer {
   asuna_ctx* ctx;
   TimedEvent te;
-  ScopedTimer(asuna_ctx* c, int kind) : ctx(c) {
+  bool on;
+  ScopedTimer(asuna_ctx* c, int kind) : ctx(c), on(c->profiling) {
+    if (!on) return;
     te.a = get_event(c);
     te.b = get_event(c);
     te.kind = kind;
     cudaEventRecord(te.a, c->stream);
   }
   ~ScopedTimer() {
+    if (!on) return;
     cudaEventRecord(te.b, ctx->stream);
     ctx->pending.push_back(te);
+    if (ctx->pending.size() >= 4096) {  // cap: drain instead of growing without bound
+      cudaEventSynchronize(te.b);
+      collect_timers(ctx);
+    }
   }
 };
 void collect_timers(asuna_ctx* ctx) {
@@ -682,6 +694,7 @@ int asuna_set_state(asuna_ctx* ctx, const AsunaState* st) {
   if (!st) return fail(ctx, ASUNA_E_INVALID, "null state");
   if (st->spp != 1) return fail(ctx, ASUNA_E_INVALID, "spp must be 1 per frame (reference tracer.cpp:211)");
   if (st->nMultiChannel > ASUNA_NUM_OUTPUT_IMAGES - 1) return fail(ctx, ASUNA_E_INVALID, "more than 8 output channels");
+  if (st->maxPathDepth > ASUNA_MAX_ITERS) return fail(ctx, ASUNA_E_INVALID, "maxPathDepth exceeds ASUNA_MAX_ITERS (256)");
   if (st->numLights < 0 || (size_t)st->numLights + 1 > std::max<size_t>(ctx->lights.size(), 1))
     return fail(ctx, ASUNA_E_INVALID, "numLights exceeds the uploaded light table");
   if (st->hasEnvMap == 1 && !ctx->env[0].d_texels) return fail(ctx, ASUNA_E_INVALID, "hasEnvMap set but no env map uploaded");
@@ -743,6 +756,8 @@ static int render_batch(asuna_ctx* ctx, const int* frames, uint32_t n_frames) {
     ASUNA_CUDA_CHECK(cudaMemcpyAsync(&alive, &ctx->d_counters->queue[iter], sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
     if (alive == 0) break;
+    if (iter + 1 >= ASUNA_MAX_ITERS)  // the reference would keep looping; say so instead of dropping live paths silently
+      return fail(ctx, ASUNA_E_UNSUPPORTED, "opacity pass-through chain exceeds ASUNA_MAX_ITERS bounce iterations");
     bounce();
   }
   {
@@ -780,6 +795,14 @@ int asuna_render_frames(asuna_ctx* ctx, uint32_t n) {
 
 static int pull_totals(asuna_ctx* ctx);
 
+// User-ray launches do not fold into Totals: fetch their overflow flag directly (the stream is idle here).
+static int check_user_overflow(asuna_ctx* ctx) {
+  uint32_t ovf = 0;
+  ASUNA_CUDA_CHECK(cudaMemcpy(&ovf, &ctx->d_counters->stack_overflow, sizeof ovf, cudaMemcpyDeviceToHost));
+  if (ovf) return fail(ctx, ASUNA_E_CUDA, "traversal stack overflow: results are incomplete");
+  return 0;
+}
+
 int asuna_sync(asuna_ctx* ctx) {
   cudaSetDevice(ctx->device);
   int rc = pull_totals(ctx);  // also surfaces a traversal stack overflow
@@ -794,6 +817,7 @@ int asuna_read_channel(asuna_ctx* ctx, int ch, float* out) {
   cudaSetDevice(ctx->device);
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(out, ctx->out.img[ch], (size_t)ctx->W * ctx->H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  collect_timers(ctx);
   return 0;
 }
 
@@ -858,6 +882,10 @@ int asuna_set_counting(asuna_ctx* ctx, int on) {
   ctx->counting = on != 0;
   return 0;
 }
+int asuna_set_profiling(asuna_ctx* ctx, int on) {
+  ctx->profiling = on != 0;
+  return 0;
+}
 int asuna_reset_stats(asuna_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -892,7 +920,7 @@ int asuna_trace_rays(asuna_ctx* ctx, const float* rays, uint32_t n, float* tuv, 
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(ip, ctx->d_user_ip, (size_t)n * 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ASUNA_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  return check_user_overflow(ctx);
 }
 int asuna_occlusion_rays(asuna_ctx* ctx, const float* rays, uint32_t n, uint8_t* occ) {
   if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
@@ -900,11 +928,12 @@ int asuna_occlusion_rays(asuna_ctx* ctx, const float* rays, uint32_t n, uint8_t*
   cudaSetDevice(ctx->device);
   int rc = upload_user_rays(ctx, rays, n);
   if (rc) return rc;
+  ASUNA_CUDA_CHECK(cudaMemsetAsync(&ctx->d_counters->stack_overflow, 0, sizeof(uint32_t), ctx->stream));
   launch_trace_user(ctx->stream, ctx->dims, ctx->view, ctx->d_user_rays, n, nullptr, nullptr, ctx->d_user_occ, ctx->d_counters);
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(occ, ctx->d_user_occ, n, cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ASUNA_CUDA_CHECK(cudaGetLastError());
-  return 0;
+  return check_user_overflow(ctx);
 }
 int asuna_trace_primary(asuna_ctx* ctx, uint32_t* ip, float* t) {
   if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
@@ -914,6 +943,7 @@ int asuna_trace_primary(asuna_ctx* ctx, uint32_t* ip, float* t) {
   int rc = upload_user_rays(ctx, nullptr, n);
   if (rc) return rc;
   FrameParams fp = make_frame_params(ctx);
+  ASUNA_CUDA_CHECK(cudaMemsetAsync(&ctx->d_counters->stack_overflow, 0, sizeof(uint32_t), ctx->stream));
   launch_primary_rays(ctx->stream, fp, ctx->d_user_rays);
   launch_trace_user(ctx->stream, ctx->dims, ctx->view, ctx->d_user_rays, n, ctx->d_user_tuv, ctx->d_user_ip, nullptr, ctx->d_counters);
   std::vector<float> tuv((size_t)n * 3);
@@ -922,7 +952,7 @@ int asuna_trace_primary(asuna_ctx* ctx, uint32_t* ip, float* t) {
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   ASUNA_CUDA_CHECK(cudaGetLastError());
   for (uint32_t i = 0; i < n; i++) t[i] = tuv[3 * (size_t)i];
-  return 0;
+  return check_user_overflow(ctx);
 }
 int asuna_accel_stats(asuna_ctx* ctx, uint64_t out[4]) {
   if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");

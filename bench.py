@@ -216,6 +216,7 @@ def main():
 
     sc = build_scene(args)
     ctx = capi.Context(gpu_id=local)  # raises without the CUDA library / a device: there is no fallback
+    ctx.set_profiling(True)  # per-kernel CUDA-event times feed the roofline block (the e2e leg below runs without)
     t0 = time.perf_counter()
     build_ms = sc.upload(ctx)
     upload_s = time.perf_counter() - t0
@@ -291,6 +292,7 @@ def main():
     h2d = cam_host.nbytes + sc.shot_state(0).nbytes + sc.sunsky.nbytes
     d2h = n_px * 16
     img = ctx.pinned_image() if rank == 0 else None  # page-locked read-back buffer (asuna_host_alloc), reused every step
+    ctx.set_profiling(False)  # what an integration gets by default: no per-launch event records
     for _ in range(2):
         sc.begin_shot(ctx, 0)
         ctx.render_frames(global_frames_per_step)

@@ -77,6 +77,7 @@ Png decode_png(const std::vector<uint8_t>& f, const std::string& name) {
     const uint8_t* d = &f[p + 8];
     if (p + 12 + len > f.size()) throw std::runtime_error(name + ": truncated PNG");
     if (type == "IHDR") {
+      if (len != 13) throw std::runtime_error(name + ": bad PNG IHDR length");
       img.w = (int)be32(d), img.h = (int)be32(d + 4);
       img.depth = d[8], color = d[9], interlace = d[12];
     } else if (type == "PLTE") plte.assign(d, d + len);
@@ -88,6 +89,14 @@ Png decode_png(const std::vector<uint8_t>& f, const std::string& name) {
   if (interlace) throw std::runtime_error(name + ": interlaced PNG is not supported");
   int spp = color == 0 ? 1 : color == 2 ? 3 : color == 3 ? 1 : color == 4 ? 2 : color == 6 ? 4 : 0;
   if (!spp || img.w <= 0 || img.h <= 0) throw std::runtime_error(name + ": bad PNG header");
+  // bit depths the PNG specification allows per colour type; anything else would divide by a zero maxval or shift
+  // by a negative amount below
+  const int dep = img.depth;
+  const bool depth_ok = color == 0 ? (dep == 1 || dep == 2 || dep == 4 || dep == 8 || dep == 16)
+                        : color == 3 ? (dep == 1 || dep == 2 || dep == 4 || dep == 8)
+                                     : (dep == 8 || dep == 16);
+  if (!depth_ok) throw std::runtime_error(name + ": bad PNG bit depth");
+  if ((uint64_t)img.w * (uint64_t)img.h > (1ull << 28)) throw std::runtime_error(name + ": PNG larger than 2^28 pixels");
   size_t bpp_bits = (size_t)spp * img.depth, stride = (img.w * bpp_bits + 7) / 8, bpp = std::max<size_t>(1, bpp_bits / 8);
   std::vector<uint8_t> raw = zlib_inflate(idat.data(), idat.size(), (stride + 1) * img.h);
   if (raw.size() != (stride + 1) * img.h) throw std::runtime_error(name + ": PNG data size mismatch");

@@ -170,7 +170,8 @@ enum AsunaError {
 };
 
 /* Counters a caller may read after a render; all are totals since the last asuna_reset_stats.
- * Times are device times from CUDA events recorded on the context's stream around each launch. */
+ * Times are device times from CUDA events recorded on the context's stream around each launch, kept only while
+ * asuna_set_profiling is on (build_ms is always measured). */
 typedef struct AsunaStats {
   uint64_t paths;          /* pixel-samples started                         */
   uint64_t closest_rays;   /* closest-hit rays traced (rgen:108)            */
@@ -271,6 +272,11 @@ int asuna_stream_handle(asuna_ctx* ctx, void** out_stream);
 /* Instrumented traversal: when on, closest-hit launches also count node visits / triangle tests
  * (slower; used to derive the algorithmic bytes per ray of the roofline, never while timing). */
 int asuna_set_counting(asuna_ctx* ctx, int on);
+
+/* Profiling: when on, every kernel group of asuna_render_frames is bracketed by a CUDA-event pair feeding the *_ms
+ * fields of AsunaStats.  Off by default (counts are always kept): an integration that renders frame after frame
+ * (reference src/tracer/tracer.cpp:218-228) records no events. */
+int asuna_set_profiling(asuna_ctx* ctx, int on);
 
 int asuna_get_stats(asuna_ctx* ctx, AsunaStats* out);
 int asuna_reset_stats(asuna_ctx* ctx);

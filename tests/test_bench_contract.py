@@ -8,6 +8,8 @@ import sys
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
 
 
 def _run(args):
@@ -23,7 +25,9 @@ def test_reference_arm_prints_one_json_line_with_the_contract_keys():
     assert d["impl"] == "reference" and d["metric"] == "1080p samples/sec" and d["unit"] == "samples/s"
     assert d["higher_is_better"] is True and d["scaling"] == "weak" and d["vs_baseline"] is None and d["dtype"] == "f32"
     assert d["value"] > 0 and d["steps"] == 1 and d["n_gpus"] == 1 and d["gpu_launches"] == 0
-    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] == "port"
+    assert set(d["cpu_baseline"]) >= {"value", "unit", "cores", "kind", "sample"} and d["cpu_baseline"]["kind"] in ("reference", "port")
+    from oracle import binding  # "reference" = oracle/_ref/libref.so (the reference GLSL compiled as C++) when it is built
+    assert (d["cpu_baseline"]["kind"] == "reference") == os.path.exists(binding.REF_LIB)
     assert d["e2e"] == {"value": d["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
 

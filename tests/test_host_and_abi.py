@@ -25,7 +25,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 
 def test_oracle_mirrors_the_same_abi(oracle_lib):
     for s in capi.ABI_SYMBOLS:
-        if s in ("channel_device_ptr", "accel_stats", "stream_handle", "set_counting", "host_alloc", "host_free"):
+        if s in ("channel_device_ptr", "accel_stats", "stream_handle", "set_counting", "set_profiling", "host_alloc", "host_free"):
             continue  # device-only introspection
         assert oracle_lib.has(s), f"oracle_{s} missing"
 

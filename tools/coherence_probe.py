@@ -14,6 +14,7 @@ which = sys.argv[1] if len(sys.argv) > 1 else "glass"
 W, H = 1920, 1080
 sc = scenes.glass_blob(W, H, subdiv=6, env_size=(64, 32)) if which == "glass" else scenes.ray_bench(W, H, subdiv=8, depth=4)
 ctx = capi.Context(gpu_id=0)
+ctx.set_profiling(True)
 sc.upload(ctx)
 sc.begin_shot(ctx, 0)
 shot = sc.shots[0]

@@ -28,6 +28,7 @@ elif which == "glass":
 else:
     sc = scenes.instanced_field(1920, 1080, subdiv=subdiv, grid=10)
 ctx = capi.Context(gpu_id=0)
+ctx.set_profiling(True)
 build_ms = sc.upload(ctx)
 acc = ctx.accel_stats()
 sc.begin_shot(ctx, 0)

@@ -33,6 +33,7 @@ for name, build in CONFIGS:
     sc = build()
     gen_s = time.perf_counter() - t0
     ctx = capi.Context(gpu_id=0)
+    ctx.set_profiling(True)
     build_ms = sc.upload(ctx)
     acc = ctx.accel_stats()
     shots = range(len(sc.shots)) if name.startswith("C5") else [0]
