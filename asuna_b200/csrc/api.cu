@@ -68,6 +68,7 @@ struct asuna_ctx {
   SceneView view{};
   BuildScratch scratch;
   uint64_t accel_stats[4] = {0, 0, 0, 0};
+  size_t pool_nodes = 0, pool_tris = 0;  // allocated entries of d_blas_nodes / d_tris (asuna_debug_download_accel)
   bool may_pass_through = false;
   uint32_t kind_mask = 0;  // hit kinds that can occur in this scene (which shade kernels to launch)
 
@@ -517,6 +518,7 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
     max_prims = std::max(max_prims, world_tris);
   }
   if (total_tris >= (1u << 27)) return fail(ctx, ASUNA_E_INVALID, "more than 2^27 triangles");
+  ctx->pool_nodes = total_nodes, ctx->pool_tris = total_tris;
   ASUNA_CUDA_CHECK(ctx->scratch.reserve(max_prims));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_blas_nodes, total_nodes * sizeof(WideNode)));
   ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_build_results, (n_mesh + 2) * sizeof(BuildResult)));
@@ -966,6 +968,22 @@ int asuna_accel_stats(asuna_ctx* ctx, uint64_t out[4]) {
 // asuna_get_stats has fetched the totals.
 int asuna_debug_lane_stats(asuna_ctx* ctx, uint64_t out[6]) {
   for (int k = 0; k < 6; k++) out[k] = ctx->h_totals->lane_stats[k];
+  return 0;
+}
+// Test hook: the node and triangle pools of the mesh-level BVHs as built (tests walk the tree on the host: child boxes
+// inside parent boxes, every primitive referenced once, quantised boxes contain their triangles).
+// sizes = {allocated nodes, triangle slots, root of the single-level world BVH or ~0}.
+int asuna_debug_accel_sizes(asuna_ctx* ctx, uint64_t sizes[3]) {
+  if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
+  sizes[0] = ctx->pool_nodes, sizes[1] = ctx->pool_tris, sizes[2] = ctx->view.single_root;
+  return 0;
+}
+int asuna_debug_download_accel(asuna_ctx* ctx, void* nodes_out, void* tris_out) {
+  if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
+  cudaSetDevice(ctx->device);
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  if (nodes_out) ASUNA_CUDA_CHECK(cudaMemcpy(nodes_out, ctx->d_blas_nodes, ctx->pool_nodes * sizeof(WideNode), cudaMemcpyDeviceToHost));
+  if (tris_out) ASUNA_CUDA_CHECK(cudaMemcpy(tris_out, ctx->d_tris, ctx->pool_tris * sizeof(TriSlot), cudaMemcpyDeviceToHost));
   return 0;
 }
 int asuna_debug_radix_sort(asuna_ctx* ctx, uint64_t* keys, uint32_t* vals, uint32_t n) {

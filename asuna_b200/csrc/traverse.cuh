@@ -145,6 +145,28 @@ ADEV void unpack4(uint32_t v, uint32_t magic, float f[4]) {
   }
 }
 
+// Two plane distances per instruction: Blackwell's packed fp32 FMA (fma.rn.f32x2 -> FFMA2; the scale and the bias are
+// broadcast from single registers).  Each half is an ordinary IEEE fp32 fma, so results equal the scalar form bit for
+// bit, and it halves the FMA share of the slab test.
+// Measured on B200 (profiles/README.md, round 2): the closest-hit kernel gets 7 % SLOWER (2.58 -> 2.41 G rays/s: the
+// 64-bit-aligned register pairs push it over its 72-register budget into spills, and FFMA2 saves no ALU-pipe work, which
+// is what binds), the shadow kernel 3.5 % faster.  Off by default.
+#ifndef ASUNA_FFMA2
+#define ASUNA_FFMA2 0
+#endif
+ADEV void fma_pair(float q0, float q1, float a, float b, float& r0, float& r1) {
+#if ASUNA_FFMA2
+  unsigned long long pq, pa, pb, pr;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(pq) : "f"(q0), "f"(q1));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
+  asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(pr) : "l"(pq), "l"(pa), "l"(pb));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r0), "=f"(r1) : "l"(pr));
+#else
+  r0 = fmaf(q0, a, b), r1 = fmaf(q1, a, b);
+#endif
+}
+
 ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 n4, const RaySpace& r, float tmin,
                                   float tmax, uint32_t magic) {
   constexpr bool kHalfNear = ASUNA_HALF_UNPACK >= 2, kHalfFar = ASUNA_HALF_UNPACK >= 1;
@@ -157,7 +179,17 @@ ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 
   const float hx = 0.50001f * fabsf(ax), hy = 0.50001f * fabsf(ay), hz = 0.50001f * fabsf(az);
   const float kBn = kHalfNear ? 1024.0f : 8388608.0f, kBf = kHalfFar ? 1024.0f : 8388608.0f;
   const float bnx = fmaf(-kBn, ax, cx) - hx, bny = fmaf(-kBn, ay, cy) - hy, bnz = fmaf(-kBn, az, cz) - hz;
+  // far planes: the ~3 ulp widening is folded into scale and bias (6 multiplies per node instead of 8 per node on
+  // the results; still conservative: each product is within half an ulp of the widened value)
+#ifdef ASUNA_FOLD_WIDEN
+  const float afx = ax * kWiden, afy = ay * kWiden, afz = az * kWiden;
+  const float bfx = (fmaf(-kBf, ax, cx) + hx) * kWiden, bfy = (fmaf(-kBf, ay, cy) + hy) * kWiden,
+              bfz = (fmaf(-kBf, az, cz) + hz) * kWiden;
+  const float kW = 1.0f;
+#else
+  const float afx = ax, afy = ay, afz = az, kW = kWiden;
   const float bfx = fmaf(-kBf, ax, cx) + hx, bfy = fmaf(-kBf, ay, cy) + hy, bfz = fmaf(-kBf, az, cz) + hz;
+#endif
   const bool nx = (r.oct & 1u) != 0u, ny = (r.oct & 2u) != 0u, nz = (r.oct & 4u) != 0u;
   const uint32_t octinv4 = (7u ^ r.oct) * 0x01010101u;
   uint32_t mask = 0;
@@ -175,16 +207,22 @@ ADEV uint32_t intersect_wide_node(uint4 n0, uint4 n1, uint4 n2, uint4 n3, uint4 
     unpack4<kHalfNear>(nx ? qhx : qlx, magic, qnx), unpack4<kHalfFar>(nx ? qlx : qhx, magic, qfx);
     unpack4<kHalfNear>(ny ? qhy : qly, magic, qny), unpack4<kHalfFar>(ny ? qly : qhy, magic, qfy);
     unpack4<kHalfNear>(nz ? qhz : qlz, magic, qnz), unpack4<kHalfFar>(nz ? qlz : qhz, magic, qfz);
-#define ASUNA_CHILD(J)                                                                                      \
+#define ASUNA_CHILD(J, TNX, TNY, TNZ, TFX, TFY, TFZ)                                                          \
     {                                                                                                         \
-      float tnx = fmaf(qnx[J], ax, bnx), tfx = fmaf(qfx[J], ax, bfx);                                         \
-      float tny = fmaf(qny[J], ay, bny), tfy = fmaf(qfy[J], ay, bfy);                                         \
-      float tnz = fmaf(qnz[J], az, bnz), tfz = fmaf(qfz[J], az, bfz);                                         \
-      float cmin = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, tmin));                                                  \
-      float cmax = fminf(fminf(fminf(tfx, tfy), tfz) * kWiden, tmax);                                         \
+      float cmin = fmaxf(fmaxf(TNX, TNY), fmaxf(TNZ, tmin));                                                  \
+      float cmax = kW == 1.0f ? fminf(fminf(TFX, TFY), fminf(TFZ, tmax)) : fminf(fminf(fminf(TFX, TFY), TFZ) * kW, tmax); \
       if (cmin <= cmax) mask |= byte_of<J>(child_bits4) << byte_of<J>(bit_index4);                            \
     }
-    ASUNA_CHILD(0) ASUNA_CHILD(1) ASUNA_CHILD(2) ASUNA_CHILD(3)
+#define ASUNA_CHILD_PAIR(J)                                                                                  \
+    {                                                                                                         \
+      float nx0, nx1, ny0, ny1, nz0, nz1, fx0, fx1, fy0, fy1, fz0, fz1;                                       \
+      fma_pair(qnx[J], qnx[J + 1], ax, bnx, nx0, nx1), fma_pair(qfx[J], qfx[J + 1], afx, bfx, fx0, fx1);      \
+      fma_pair(qny[J], qny[J + 1], ay, bny, ny0, ny1), fma_pair(qfy[J], qfy[J + 1], afy, bfy, fy0, fy1);      \
+      fma_pair(qnz[J], qnz[J + 1], az, bnz, nz0, nz1), fma_pair(qfz[J], qfz[J + 1], afz, bfz, fz0, fz1);      \
+      ASUNA_CHILD(J, nx0, ny0, nz0, fx0, fy0, fz0) ASUNA_CHILD(J + 1, nx1, ny1, nz1, fx1, fy1, fz1)           \
+    }
+    ASUNA_CHILD_PAIR(0) ASUNA_CHILD_PAIR(2)
+#undef ASUNA_CHILD_PAIR
 #undef ASUNA_CHILD
   }
   return mask;
@@ -222,24 +260,51 @@ ADEV void lane_begin(Lane& L, const SceneView& sc, float3 o, float3 d, float tmi
   L.best.inst = 0xFFFFFFFFu, L.best.prim = 0xFFFFFFFFu, L.best.b1 = L.best.b2 = L.best.t = 0.f;
 }
 
-// stack[k] holds entry k - 1 (slot 0 is a dummy), so push and pop need no "is there an entry below" branch
-ADEV void lane_push(Lane& L, uint2* stack, uint2 e, uint32_t* overflow) {
+// Where the stack entries below the register-resident top live.  Default: a per-thread local-memory array (L1-cached,
+// 64-bit STL / LDL).  ASUNA_SMEM_STACK = N > 0 is the "short shared-memory stack" variant BASELINE.json's north star
+// names: the N entries nearest the top of an empty stack sit in shared memory ([entry][thread] layout, conflict-free),
+// deeper ones overflow to the local array.  Measured on B200 (profiles/README.md, round 2) -- see there for why the
+// local-memory form stays the default.
+#ifndef ASUNA_SMEM_STACK
+#define ASUNA_SMEM_STACK 0
+#endif
+struct StackMem {
+  uint2* local;
+#if ASUNA_SMEM_STACK > 0
+  uint2* shared;  // &smem[threadIdx.x], stride kTraceThreads
+#endif
+  ADEV void store(int i, uint2 e) const {
+#if ASUNA_SMEM_STACK > 0
+    if (i < ASUNA_SMEM_STACK) shared[i * kTraceThreads] = e;
+    else
+#endif
+      local[i] = e;
+  }
+  ADEV uint2 load(int i) const {
+#if ASUNA_SMEM_STACK > 0
+    if (i < ASUNA_SMEM_STACK) return shared[i * kTraceThreads];
+#endif
+    return local[i];
+  }
+};
+// entry k of the storage holds stack entry k - 1 (slot 0 is a dummy), so push and pop need no "is there an entry below" branch
+ADEV void lane_push(Lane& L, const StackMem& stack, uint2 e, uint32_t* overflow) {
   if (L.sp < kStackSize) {
-    stack[L.sp++] = L.top;
+    stack.store(L.sp++, L.top);
     L.top = e;
   } else {
     atomicAdd(overflow, 1u);
   }
 }
-ADEV uint2 lane_pop(Lane& L, const uint2* stack) {
+ADEV uint2 lane_pop(Lane& L, const StackMem& stack) {
   const uint2 e = L.top;
-  L.top = stack[--L.sp];
+  L.top = stack.load(--L.sp);
   return e;
 }
 
 // One wide-node step: take the nearest pending child of the current node group, test its eight children.
 template <bool COUNT, bool SINGLE>
-ADEV void lane_node_step(Lane& L, uint2* stack, const SceneView& sc, uint32_t* overflow, uint32_t& n_nodes) {
+ADEV void lane_node_step(Lane& L, const StackMem& stack, const SceneView& sc, uint32_t* overflow, uint32_t& n_nodes) {
   const uint32_t hits = L.ng.y;
   const uint32_t bit = 31u - (uint32_t)__clz(hits);
   uint2 rest = make_uint2(L.ng.x, hits & ~(1u << bit));
@@ -259,7 +324,7 @@ ADEV void lane_node_step(Lane& L, uint2* stack, const SceneView& sc, uint32_t* o
 }
 
 // Instance group at the top level: enter its first instance, keep the rest (and the pending node group) for later.
-ADEV void lane_enter_instance(Lane& L, uint2* stack, const SceneView& sc, uint32_t* overflow) {
+ADEV void lane_enter_instance(Lane& L, const StackMem& stack, const SceneView& sc, uint32_t* overflow) {
   const uint32_t k = (uint32_t)__ffs((int)L.tg.y) - 1u;
   L.tg.y &= L.tg.y - 1u;
   if (L.sp + 2 > kStackSize) {
@@ -329,7 +394,13 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
   uint32_t* const stg = STAGE ? stage_words + (threadIdx.x >> 5) * (kStageWords * 32) + lane : nullptr;
   bool staged = false;
   Lane L;
-  uint2 stack[kStackSize + 1];
+  uint2 stack_local[kStackSize + 1];
+  StackMem stack;
+  stack.local = stack_local;
+#if ASUNA_SMEM_STACK > 0
+  __shared__ uint2 stack_shared[ASUNA_SMEM_STACK * kTraceThreads];
+  stack.shared = stack_shared + threadIdx.x;
+#endif
   L.sp = 0, L.blas_sp = 0, L.in_blas = false, L.shear_ok = false;
   L.ng = L.tg = L.top = make_uint2(0u, 0u);
   bool active = false, exhausted = (count == 0) || sc.n_instances == 0;

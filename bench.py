@@ -17,8 +17,16 @@ rank 0 with one NCCL reduce and resolved there.
             step's camera / state / sun-sky structs from host memory, renders, resolves (NCCL reduce at
             N > 1) and reads the radiance image back into host memory (a complete mini-shot).
 `roofline`: closest-hit trace kernel (dominant): algorithmic bytes per ray (32 B ray in +
-            16 B hit out + visited nodes x 64 B + tested triangles x 48 B, counts from an untimed
-            instrumented pass over the same BVH) x rays per launch / mean launch time (CUDA events).
+            16 B hit out + visited nodes x 80 B + tested triangles x 48 B, counts from an untimed
+            instrumented pass over the same BVH) x rays per launch / mean launch time (CUDA events).  The contract's
+            fraction is against the HBM copy peak; the kernel's working set is L2-resident and what binds it is SM issue
+            / the ALU pipe, so `issue_frac`, `alu_pipe_frac` and `lanes_per_inst` from the committed single-launch ncu
+            capture (profiles/traffic.json) are carried beside it.
+`multi_gpu_check` (N > 1): rank 0 renders the same frames alone and compares with the NCCL-reduced image.
+`time_to_image_s`: the WHOLE 256-spp job of BASELINE configs[1] at N ranks (strong scaling): context creation, scene
+            upload, BVH build, 256 / N frames per rank, NCCL reduce, resolve, read-back into host memory.
+`ray_bench` (rank 0): the north star's other two figures -- incoherent closest-hit Mrays/s on the 1.31 M-triangle C4'
+            scene with nodes / triangles per ray, and BVH build ms at 1.31 M and 32.8 M triangles.
 """
 import argparse
 import json
@@ -113,12 +121,15 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the dominant kernel from the committed ncu --set full capture, if any."""
+def ncu_capture():
+    """Numbers of the dominant kernel from the committed single-launch `ncu --set full` capture (profiles/traffic.json:
+    DRAM bytes per launch, issue-slot and ALU-pipe fractions, live lanes per instruction), if any."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        return json.load(open(p)).get("k_trace_closest_dram_bytes_per_launch")
-    return None
+    return json.load(open(p)) if os.path.exists(p) else {}
+
+
+def ncu_traffic():
+    return ncu_capture().get("k_trace_closest_dram_bytes_per_launch")
 
 
 # ----------------------------------------------------------------------------- CPU arm
@@ -185,6 +196,8 @@ def main():
     ap.add_argument("--workload", default="glass", choices=["glass", "field4k"],
                     help="glass = BASELINE configs[1] (the bench line); field4k = configs[3], for scaling runs of the instanced 4K scene")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-ray-bench", action="store_true", help="skip the C4' ray bench / 32.8 M-triangle build / time-to-image extras")
+    ap.add_argument("--tti-spp", type=int, default=256, help="samples per pixel of the time-to-image job (BASELINE configs[1]: 256)")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0)
     args = ap.parse_args()
     if args.workload == "field4k":
@@ -314,8 +327,108 @@ def main():
     e2e_value = samples / (e2e_ms / 1e3)
     clock_info = clocks.stop() if rank == 0 else None
 
+    # ---- multi-GPU correctness through the real NCCL path: the reduced image of N partitions against the same
+    # frames rendered by rank 0 alone (same seeds per (pixel, frame); only the fp32 summation order differs)
+    multi_gpu_check = None
+    if world > 1:
+        sc.begin_shot(ctx, 0)
+        ctx.render_frames(global_frames_per_step)
+        resolve()
+        if rank == 0:
+            reduced = ctx.read_channel(0).copy()
+            ctx.set_partition(0, 1)
+            sc.begin_shot(ctx, 0)
+            ctx.render_frames(global_frames_per_step)
+            ctx.sync()
+            alone = ctx.read_channel(0)
+            ctx.set_partition(rank, world)
+            a, b = reduced[..., :3].astype(np.float64), alone[..., :3].astype(np.float64)
+            rel = np.abs(a - b) / np.maximum(np.abs(b), 1e-3)
+            multi_gpu_check = {"frames": global_frames_per_step, "max_rel_err": float(rel.max()), "rtol": 3e-5,
+                               "mean_reduced": float(a.mean()), "mean_single_gpu": float(b.mean()),
+                               "pass": bool(rel.max() <= 3e-5)}
+            if not multi_gpu_check["pass"]:
+                raise SystemExit(f"multi-GPU image differs from the single-GPU image: {multi_gpu_check}")
+        barrier()
+
+    # ---- time to image: the whole 256-spp job of BASELINE configs[1] at `world` ranks (strong scaling), everything a
+    # user waits for after the scene description is in host memory: context, upload, BVH build, 256 / N frames per
+    # rank, reduce + resolve, read-back
+    tti = None
+    if not args.no_ray_bench and args.workload == "glass":
+        ctx.close()
+        barrier()
+        t0 = time.perf_counter()
+        ctx = capi.Context(gpu_id=local)
+        t1 = time.perf_counter()
+        tti_build_ms = sc.upload(ctx)
+        ctx.set_partition(rank, world)
+        t2 = time.perf_counter()
+        sc.begin_shot(ctx, 0)
+        ctx.render_frames(args.tti_spp)
+        ctx.sync()
+        t3 = time.perf_counter()
+        resolve()
+        if rank == 0:
+            img = ctx.pinned_image()
+            ctx.read_channel(0, out=img)
+        t4 = time.perf_counter()
+        barrier()
+        t5 = time.perf_counter()
+        tt = torch.tensor([t5 - t0, t1 - t0, t2 - t1, t3 - t2, t4 - t3], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        tt = tt.tolist()
+        tti = {"value": tt[0], "unit": "s", "spp": args.tti_spp, "scaling": "strong",
+               "create_context_s": tt[1], "upload_and_build_s": tt[2], "bvh_build_ms": tti_build_ms, "render_s": tt[3],
+               "reduce_resolve_readback_s": tt[4],
+               "samples_per_s": args.tti_spp * n_px / tt[0]}
+
+    # ---- the north star's other figures, rank 0 only: C4' (1.31 M triangles) incoherent rays/s, BVH build at 1.31 M and
+    # 32.8 M triangles
+    ray_bench = None
+    if not args.no_ray_bench and rank == 0:
+        from asuna_b200 import scenes
+        ctx.close()
+        rb = scenes.ray_bench(1920, 1080, subdiv=8, depth=4)
+        c2 = capi.Context(gpu_id=local)
+        c2.set_profiling(True)
+        rb_build_ms = rb.upload(c2)
+        rb.begin_shot(c2, 0)
+        c2.set_counting(True)
+        c2.render_frames(1)
+        s1 = c2.stats()
+        c2.set_counting(False)
+        rb.begin_shot(c2, 0)
+        c2.render_frames(8)
+        c2.sync()
+        c2.reset_stats()
+        c2.render_frames(16)
+        s2 = c2.stats()
+        ray_bench = {"scene": "C4': 1.31 M-triangle blob + ground, lambertian, white environment, 1920x1080, depth 4, 16 frames",
+                     "triangles": int(sum(len(i) // 3 for _, i in rb.meshes)),
+                     "incoherent_mrays_per_s": s2["incoherent_closest_rays"] / max(s2["closest_ms"], 1e-9) / 1e3 *
+                                               1.0,
+                     "closest_mrays_per_s": s2["closest_rays"] / max(s2["closest_ms"], 1e-9) / 1e3,
+                     "all_mrays_per_s": (s2["closest_rays"] + s2["shadow_rays"]) / max(s2["trace_ms"], 1e-9) / 1e3,
+                     "samples_per_s": s2["paths"] / max(s2["total_ms"], 1e-9) * 1e3,
+                     "nodes_per_ray": s1["node_visits"] / max(s1["closest_rays"], 1),
+                     "tris_per_ray": s1["tri_tests"] / max(s1["closest_rays"], 1),
+                     "bvh_build_ms": rb_build_ms,
+                     "note": "incoherent = closest-hit rays at depth >= 2 (after a cosine-hemisphere bounce) over the closest-hit kernel's device time"}
+        c2.close()
+        del rb
+        fld = scenes.instanced_field(256, 144, spp=1, depth=5, subdiv=7, grid=10)
+        c3 = capi.Context(gpu_id=local)
+        ray_bench["bvh_build_ms_32M"] = fld.upload(c3)
+        ray_bench["triangles_32M"] = int(sum(len(fld.meshes[m][1]) // 3 for _, m, _, _ in fld.instances))
+        c3.close()
+        del fld
+    barrier()
+
     if rank == 0:
         peak, peak_src = measured_peak()
+        cap = ncu_capture()
         rays_per_launch = st["closest_rays"] / max(st["closest_launches"], 1)
         launch_ms = st["closest_ms"] / max(st["closest_launches"], 1)
         achieved = bytes_per_ray * rays_per_launch / (launch_ms * 1e-3) / 1e9 if launch_ms > 0 else 0.0
@@ -331,6 +444,11 @@ def main():
             "clocks": clock_info,
             "roofline": {"kernel": "k_trace_closest", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": ncu_traffic(), "peak_source": peak_src,
+                         # what actually binds this kernel (its working set is L1/L2-resident): from the committed
+                         # single-launch ncu --set full capture of this build
+                         "actual_bound": "sm_issue / alu_pipe", "issue_frac": cap.get("k_trace_closest_issue_frac"),
+                         "alu_pipe_frac": cap.get("k_trace_closest_alu_pipe_frac"),
+                         "lanes_per_inst": cap.get("k_trace_closest_lanes_per_inst"), "ncu_source": cap.get("source"),
                          "bytes_per_ray": bytes_per_ray, "nodes_per_ray": nodes_per_ray, "tris_per_ray": tris_per_ray,
                          "rays_per_launch": rays_per_launch, "launch_ms": launch_ms,
                          "kernel_share_of_step": st["closest_ms"] / max(st["total_ms"], 1e-9),
@@ -344,12 +462,19 @@ def main():
             "bvh_build_ms": build_ms, "scene_upload_s": upload_s,
             "kernel_ms_rank0": {k: st[k] for k in ("closest_ms", "shadow_ms", "shade_ms", "total_ms")},
         }
+        if multi_gpu_check is not None:
+            line["multi_gpu_check"] = multi_gpu_check
+        if tti is not None:
+            line["time_to_image_s"] = tti["value"]
+            line["time_to_image"] = tti
+        if ray_bench is not None:
+            line["ray_bench"] = ray_bench
         if world == 1 and not args.no_cpu_baseline:
             r = cpu_run(args, 64, 1, budget_s=args.cpu_budget_s)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
         json_out.write(json.dumps(line) + "\n")
         json_out.flush()
-    ctx.close()
+    ctx.close()  # idempotent
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

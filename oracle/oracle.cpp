@@ -1859,6 +1859,12 @@ int oracle_trace_primary(oracle_ctx* c, uint32_t* ip, float* t) {
 }
 
 // ---- unit-test hooks: expose individual restated functions so tests can pin them ----
+// SAH cost of mesh `mesh`'s binned-SAH BVH2 after the optimal 8-wide collapse (bvh.h wide_sah_cost): the quality
+// yardstick for the GPU builder (tests/test_gpu_kernels.py).
+double oracle_wide_sah_cost(oracle_ctx* c, uint32_t mesh, double c_node, double c_prim, uint32_t pmax) {
+  if (mesh >= c->meshes.size()) return -1.0;
+  return c->meshes[mesh].bvh.wide_sah_cost(c_node, c_prim, pmax);
+}
 // n independent closest-hit (inst/prim/b1/b2 given) or miss (inst = 0xFFFFFFFF) shader invocations on caller-made payloads.
 static int shade_probe_one(oracle_ctx* c, uint32_t inst, uint32_t prim, float b1, float b2, ShadeProbe* q) {
   const bool is_hit = inst != 0xFFFFFFFFu;

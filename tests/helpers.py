@@ -201,3 +201,75 @@ def random_material(rng, mtype, texture_ids):
     elif mtype == S.MAT_DISNEY:
         m["rhoSpec"][0] = opacity
     return m
+
+
+# ----------------------------------------------------------------------------- compressed wide BVH, walked on the host
+WIDE_NODE = np.dtype([("p", "f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "u4"), ("prim_base", "u4"),
+                      ("meta", "u1", 8), ("qlo", "u1", (3, 8)), ("qhi", "u1", (3, 8))])  # asuna_b200/csrc/device_types.cuh
+TRI_SLOT = np.dtype([("v0", "f4", 3), ("prim", "u4"), ("v1", "f4", 3), ("inst", "u4"), ("v2", "f4", 3), ("pad", "u4")])
+assert WIDE_NODE.itemsize == 80 and TRI_SLOT.itemsize == 48
+
+
+def download_accel(ctx):
+    sizes = (_C.c_uint64 * 3)()
+    ctx.L.lib.asuna_debug_accel_sizes(ctx.h, sizes)
+    nodes, tris = np.zeros(sizes[0], WIDE_NODE), np.zeros(sizes[1], TRI_SLOT)
+    rc = ctx.L.lib.asuna_debug_download_accel(ctx.h, nodes.ctypes.data_as(_C.c_void_p), tris.ctypes.data_as(_C.c_void_p))
+    assert rc == 0
+    return nodes, tris, int(sizes[2])
+
+
+def walk_wide_bvh(nodes, tris, root, c_node=1.0, c_prim=1.0):
+    """Breadth-first walk of one compressed 8-wide BVH.  Returns
+      refs        : how often each triangle slot is referenced by a leaf child,
+      outside     : number of triangle vertices outside the decoded box of ANY ancestor slot (must be 0: the boxes are
+                    conservative at every level, which is what makes the quantised slab test safe),
+      nodes_used, max_depth, sah (sum over slots of area x cost, / root area, from the decoded boxes)."""
+    refs = np.zeros(len(tris), np.int64)
+    frontier = np.array([root], np.int64)
+    clip_lo = np.full((1, 3), -np.inf)
+    clip_hi = np.full((1, 3), np.inf)
+    outside = nodes_used = depth = 0
+    sah = 0.0
+    root_area = None
+    below = (1 << np.arange(8)) - 1
+    while frontier.size:
+        depth += 1
+        nodes_used += frontier.size
+        nd = nodes[frontier]
+        scale = (nd["e"].astype(np.uint32) << 23).view(np.float32).astype(np.float64)  # (n, 3)
+        p = nd["p"].astype(np.float64)
+        lo = p[:, :, None] + nd["qlo"].astype(np.float64) * scale[:, :, None]  # (n, 3, 8)
+        hi = p[:, :, None] + nd["qhi"].astype(np.float64) * scale[:, :, None]
+        meta = nd["meta"].astype(np.int64)  # (n, 8)
+        used = meta != 0
+        inner = used & ((meta & 31) >= 24)
+        leaf = used & ~inner
+        lo = np.maximum(lo, clip_lo[:, :, None])
+        hi = np.minimum(hi, clip_hi[:, :, None])
+        ext = np.maximum(hi - lo, 0.0)
+        area = ext[:, 0] * ext[:, 1] + ext[:, 1] * ext[:, 2] + ext[:, 2] * ext[:, 0]  # (n, 8)
+        if root_area is None:
+            ulo, uhi = np.where(used[:, None, :], lo, np.inf).min(axis=2), np.where(used[:, None, :], hi, -np.inf).max(axis=2)
+            e = uhi[0] - ulo[0]
+            root_area = e[0] * e[1] + e[1] * e[2] + e[2] * e[0]
+            sah += root_area * c_node
+        count = np.where(leaf, ((meta >> 5) & 1) + ((meta >> 6) & 1) + ((meta >> 7) & 1), 0)
+        sah += float((area * inner).sum() * c_node + (area * count).sum() * c_prim)
+        # leaves: triangles inside the running intersection of all ancestor boxes
+        ni, si = np.nonzero(leaf)
+        for k in range(3):
+            sel = count[ni, si] > k
+            a, s = ni[sel], si[sel]
+            slot = nd["prim_base"][a].astype(np.int64) + (meta[a, s] & 31) + k
+            np.add.at(refs, slot, 1)
+            for v in ("v0", "v1", "v2"):
+                x = tris[v][slot].astype(np.float64)
+                outside += int(((x < lo[a, :, s]) | (x > hi[a, :, s])).any(axis=1).sum())
+        # inner children: next frontier with their clip boxes
+        ni, si = np.nonzero(inner)
+        rel = np.array([bin(int(m) & int(b)).count("1") for m, b in zip(nd["imask"][ni], below[si])], np.int64) if ni.size else np.zeros(0, np.int64)
+        assert ((nd["imask"][ni].astype(np.int64) >> si) & 1).all(), "inner slot not in imask"
+        frontier = nd["child_base"][ni].astype(np.int64) + rel
+        clip_lo, clip_hi = lo[ni, :, si], hi[ni, :, si]
+    return {"refs": refs, "outside": outside, "nodes_used": nodes_used, "max_depth": depth, "sah": sah / root_area}

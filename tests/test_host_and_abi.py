@@ -132,3 +132,24 @@ def test_flip_metric_behaves():
     assert metrics.flip(a, a) == 0.0
     assert metrics.flip(a, a + 0.0005) < 0.01 < metrics.flip(a, a + 0.01) < metrics.flip(a, np.zeros_like(a))
     assert metrics.mean_relative_error(a * 1.005, a) == pytest.approx(0.005, rel=1e-6)
+
+
+def test_header_is_c_and_every_symbol_links_from_c(tmp_path):
+    """tests/abi_smoke.c: include/asuna_b200.h must parse as C11 (-pedantic -Werror) and every declared entry point must
+    resolve against libasuna_b200.so from a plain C program (extern "C", no C++ types in the signatures)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    assert gcc, "gcc is part of the image"
+    src = os.path.join(ROOT, "tests", "abi_smoke.c")
+    text = open(src).read()
+    for s in capi.ABI_SYMBOLS:
+        assert f"TAKE(asuna_{s})" in text, f"tests/abi_smoke.c does not reference asuna_{s}"
+    exe = str(tmp_path / "abi_smoke")
+    libdir = os.path.dirname(capi.PRODUCT_LIB)
+    subprocess.check_call([gcc, "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), src, "-o", exe,
+                           "-L", libdir, "-lasuna_b200", f"-Wl,-rpath,{libdir}"])
+    out = subprocess.run([exe], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    fields = [int(x) for x in out.stdout.split()]
+    assert fields[0] == len(capi.ABI_SYMBOLS) and tuple(fields[1:7]) == S.EXPECTED_SIZES == tuple(fields[7:13])
