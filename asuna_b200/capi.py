@@ -22,7 +22,7 @@ ABI_SYMBOLS = (
     "abi_sizes", "create", "destroy", "last_error", "set_film", "add_texture", "set_envmap", "add_mesh",
     "add_material", "set_lights", "add_instance", "build_accel", "set_camera", "set_sunsky", "set_state",
     "reset_frame", "render_frames", "set_partition", "sync", "read_channel", "export_partial",
-    "import_partial", "host_alloc", "host_free", "channel_device_ptr", "stream_handle", "set_counting", "set_profiling", "get_stats", "reset_stats", "trace_primary", "trace_rays",
+    "import_partial", "post_process", "host_alloc", "host_free", "channel_device_ptr", "stream_handle", "set_counting", "set_profiling", "get_stats", "reset_stats", "trace_primary", "trace_rays",
     "occlusion_rays", "accel_stats")
 
 
@@ -167,6 +167,13 @@ class Context:
             out = np.empty((self.height, self.width, 4), np.float32)
         assert out.dtype == np.float32 and out.size == self.height * self.width * 4 and out.flags.c_contiguous
         self._call("read_channel", C.c_int(ch), _ptr(out))
+        return out
+
+    def post_process(self, post):
+        """Tone-mapped radiance image, (h, w, 4) float32 (≙ PipelinePost::run + offline colour read-back)."""
+        p = np.array(post, S.Post)
+        out = np.empty((self.height, self.width, 4), np.float32)
+        self._call("post_process", _ptr(p), _ptr(out))
         return out
 
     def pinned_image(self):

@@ -83,6 +83,14 @@ struct asuna_ctx {
   bool have_accum = false;
   OutputImages out{};
   float4* d_partial = nullptr;
+  float4* d_ldr = nullptr;        // post-processed (tone-mapped) image
+  double* d_post_sums = nullptr;  // block sums of the image mean (custom tone mapper's auto-exposure)
+  void* film_arena = nullptr;   // the nine planes + the partial-sum plane: one allocation
+  void* path_arena = nullptr;   // the whole wavefront state: one allocation
+  void* scene_arena = nullptr;  // nodes, triangle slots and the flat scene tables: one allocation per build
+  cudaStream_t upload_stream = nullptr;  // H2D copies of textures / env tables / meshes overlap the BVH build
+  cudaEvent_t ev_geometry = nullptr, ev_textures = nullptr, ev_partial = nullptr;
+  bool textures_pending = false;
 
   // wavefront buffers
   PathState ps{};
@@ -125,6 +133,32 @@ void free_dev(T*& p) {
   if (p) cudaFree(p);
   p = nullptr;
 }
+
+// Sizes first, then one cudaMalloc and the pointers into it (a 1080p context used to pay ~50 cudaMalloc calls before its
+// first frame; each costs 0.1-2 ms of host time that no amount of GPU parallelism gives back).
+struct ArenaPlan {
+  struct Item {
+    void** p;
+    size_t bytes;
+  };
+  std::vector<Item> items;
+  template <class T>
+  void add(T*& p, size_t bytes) {
+    items.push_back({reinterpret_cast<void**>(&p), bytes});
+  }
+  cudaError_t commit(void** arena) {
+    size_t total = 0;
+    for (auto& it : items) total += (it.bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(arena, std::max<size_t>(total, 256));
+    if (e != cudaSuccess) return e;
+    size_t off = 0;
+    for (auto& it : items) {
+      *it.p = static_cast<char*>(*arena) + off;
+      off += (it.bytes + 255) & ~(size_t)255;
+    }
+    return cudaSuccess;
+  }
+};
 
 cudaEvent_t get_event(asuna_ctx* ctx) {
   if (!ctx->event_pool.empty()) {
@@ -177,35 +211,22 @@ void collect_timers(asuna_ctx* ctx) {
 }
 
 void free_scene_device(asuna_ctx* ctx) {
-  free_dev(ctx->d_blas_nodes);
-  free_dev(ctx->d_tlas_nodes);
-  free_dev(ctx->d_tris);
-  free_dev(ctx->d_tlas_leaf_inst);
-  free_dev(ctx->d_tlas_ids);
-  free_dev(ctx->d_instances);
-  free_dev(ctx->d_meshes);
-  free_dev(ctx->d_materials);
-  free_dev(ctx->d_lights);
-  free_dev(ctx->d_textures);
-  free_dev(ctx->d_mesh_lo);
-  free_dev(ctx->d_mesh_hi);
-  free_dev(ctx->d_build_results);
+  free_dev(ctx->scene_arena);
+  ctx->d_blas_nodes = ctx->d_tlas_nodes = nullptr;
+  ctx->d_tris = nullptr;
+  ctx->d_tlas_leaf_inst = ctx->d_tlas_ids = nullptr;
+  ctx->d_instances = nullptr;
+  ctx->d_meshes = nullptr;
+  ctx->d_materials = nullptr;
+  ctx->d_lights = nullptr;
+  ctx->d_textures = nullptr;
+  ctx->d_mesh_lo = ctx->d_mesh_hi = nullptr;
+  ctx->d_build_results = nullptr;
 }
 
 void free_path_buffers(asuna_ctx* ctx) {
-  free_dev(ctx->ps.ray_o);
-  free_dev(ctx->ps.ray_d);
-  free_dev(ctx->ps.thr);
-  free_dev(ctx->ps.rad);
-  free_dev(ctx->ps.hit);
-  free_dev(ctx->ps.sh_o);
-  free_dev(ctx->ps.sh_d);
-  free_dev(ctx->ps.sh_l);
-  free_dev(ctx->ps.queue[0]);
-  free_dev(ctx->ps.queue[1]);
-  free_dev(ctx->ps.kind);
-  free_dev(ctx->ps.sorted);
-  free_dev(ctx->ps.bin_hist);
+  free_dev(ctx->path_arena);
+  ctx->ps = PathState{};
   ctx->path_capacity = 0;
 }
 
@@ -213,19 +234,15 @@ int ensure_path_buffers(asuna_ctx* ctx, uint32_t n_paths) {
   if (n_paths <= ctx->path_capacity) return 0;
   free_path_buffers(ctx);
   size_t n = n_paths;
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.ray_o, n * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.ray_d, n * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.thr, n * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.rad, n * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.hit, n * sizeof(uint4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sh_o, n * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sh_d, n * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sh_l, n * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.queue[0], n * sizeof(uint32_t)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.queue[1], n * sizeof(uint32_t)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.kind, n));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.sorted, n * sizeof(uint32_t)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->ps.bin_hist, ((n + kBinTile - 1) / kBinTile) * kNumKinds * sizeof(uint32_t)));
+  ArenaPlan plan;
+  plan.add(ctx->ps.ray_o, n * sizeof(float4)), plan.add(ctx->ps.ray_d, n * sizeof(float4));
+  plan.add(ctx->ps.thr, n * sizeof(float4)), plan.add(ctx->ps.rad, n * sizeof(float4));
+  plan.add(ctx->ps.hit, n * sizeof(uint4));
+  plan.add(ctx->ps.sh_o, n * sizeof(float4)), plan.add(ctx->ps.sh_d, n * sizeof(float4)), plan.add(ctx->ps.sh_l, n * sizeof(float4));
+  plan.add(ctx->ps.queue[0], n * sizeof(uint32_t)), plan.add(ctx->ps.queue[1], n * sizeof(uint32_t));
+  plan.add(ctx->ps.kind, n), plan.add(ctx->ps.sorted, n * sizeof(uint32_t));
+  plan.add(ctx->ps.bin_hist, ((n + kBinTile - 1) / kBinTile) * kNumKinds * sizeof(uint32_t));
+  ASUNA_CUDA_CHECK(plan.commit(&ctx->path_arena));
   ctx->path_capacity = n_paths;
   return 0;
 }
@@ -295,8 +312,29 @@ void asuna_abi_sizes(uint32_t out[6]) {
   out[3] = sizeof(AsunaCamera), out[4] = sizeof(AsunaState), out[5] = sizeof(AsunaSunSky);
 }
 
+// ASUNA_TIMING=1: host-side wall time of the steps of asuna_create / asuna_build_accel on stderr (developer probe for
+// the serial part of a job, tools/upload_probe.py)
+static double wall_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+struct StepTimer {
+  bool on = getenv("ASUNA_TIMING") != nullptr;
+  double t = wall_ms();
+  const char* what;
+  explicit StepTimer(const char* w) : what(w) {}
+  void step(const char* name) {
+    if (!on) return;
+    double n = wall_ms();
+    fprintf(stderr, "[asuna timing] %s: %s %.3f ms\n", what, name, n - t);
+    t = n;
+  }
+};
+
 int asuna_create(asuna_ctx** out, int gpu_id) {
   *out = nullptr;
+  StepTimer tm("create");
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || gpu_id < 0 || gpu_id >= n) return ASUNA_E_NO_DEVICE;
   if (cudaSetDevice(gpu_id) != cudaSuccess) return ASUNA_E_NO_DEVICE;
@@ -308,15 +346,25 @@ int asuna_create(asuna_ctx** out, int gpu_id) {
     return ASUNA_E_NO_DEVICE;
   }
   ctx->sm_count = prop.multiProcessorCount;
+  tm.step("device properties");
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&ctx->upload_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_geometry, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_textures, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&ctx->ev_partial, cudaEventDisableTiming) != cudaSuccess ||
       cudaMalloc(&ctx->d_counters, sizeof(Counters)) != cudaSuccess ||
       cudaMalloc(&ctx->d_totals, sizeof(Totals)) != cudaSuccess ||
       cudaMemset(ctx->d_totals, 0, sizeof(Totals)) != cudaSuccess ||
-      cudaMallocHost(&ctx->h_totals, sizeof(Totals)) != cudaSuccess ||
-      query_launch_dims(ctx->dims, ctx->sm_count) != cudaSuccess) {
+      cudaMallocHost(&ctx->h_totals, sizeof(Totals)) != cudaSuccess) {
     delete ctx;
     return ASUNA_E_CUDA;
   }
+  tm.step("streams, events, counters");
+  if (query_launch_dims(ctx->dims, ctx->sm_count) != cudaSuccess) {
+    delete ctx;
+    return ASUNA_E_CUDA;
+  }
+  tm.step("occupancy queries");
   ctx->pc.curFrame = -1;
   ctx->pc.spp = 1;
   ctx->pc.maxPathDepth = 3;
@@ -331,8 +379,11 @@ void asuna_destroy(asuna_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
   collect_timers(ctx);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
+  for (cudaEvent_t e : {ctx->ev_geometry, ctx->ev_textures, ctx->ev_partial})
+    if (e) cudaEventDestroy(e);
   free_scene_device(ctx);
   free_path_buffers(ctx);
   for (auto& t : ctx->textures) free_dev(t.d_texels);
@@ -341,8 +392,7 @@ void asuna_destroy(asuna_ctx* ctx) {
     free_dev(m.d_vertices);
     free_dev(m.d_indices);
   }
-  for (auto& p : ctx->out.img) free_dev(p);
-  free_dev(ctx->d_partial);
+  free_dev(ctx->film_arena);
   free_dev(ctx->d_counters);
   free_dev(ctx->d_totals);
   free_dev(ctx->d_sky);
@@ -353,6 +403,7 @@ void asuna_destroy(asuna_ctx* ctx) {
   if (ctx->h_totals) cudaFreeHost(ctx->h_totals);
   ctx->scratch.release();
   cudaStreamDestroy(ctx->stream);
+  if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
   delete ctx;
 }
 
@@ -363,13 +414,15 @@ int asuna_set_film(asuna_ctx* ctx, uint32_t w, uint32_t h) {
   cudaSetDevice(ctx->device);
   ctx->W = w, ctx->H = h;
   size_t bytes = (size_t)w * h * sizeof(float4);
-  for (auto& p : ctx->out.img) {
-    free_dev(p);
-    ASUNA_CUDA_CHECK(cudaMalloc(&p, bytes));
-    ASUNA_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, ctx->stream));
-  }
-  free_dev(ctx->d_partial);
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_partial, bytes));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  free_dev(ctx->film_arena);
+  ArenaPlan plan;
+  for (auto& p : ctx->out.img) plan.add(p, bytes);
+  plan.add(ctx->d_partial, bytes);
+  plan.add(ctx->d_ldr, bytes);
+  plan.add(ctx->d_post_sums, 3 * 296 * sizeof(double));
+  ASUNA_CUDA_CHECK(plan.commit(&ctx->film_arena));
+  ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->film_arena, 0, ((bytes + 255) & ~(size_t)255) * ASUNA_NUM_OUTPUT_IMAGES, ctx->stream));
   ctx->have_accum = false;
   return 0;
 }
@@ -378,7 +431,11 @@ static int upload_texture(asuna_ctx* ctx, HostTexture& t, const float* rgba, uin
   free_dev(t.d_texels);
   t.w = w, t.h = h;
   ASUNA_CUDA_CHECK(cudaMalloc(&t.d_texels, (size_t)w * h * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMemcpy(t.d_texels, rgba, (size_t)w * h * sizeof(float4), cudaMemcpyHostToDevice));
+  // On the upload stream: the call returns once the host buffer has been consumed (pageable memory is staged by the
+  // driver, so the pointer may be reused at once), the DMA itself overlaps whatever the caller does next -- usually
+  // asuna_build_accel.  Rendering waits for ev_textures.
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(t.d_texels, rgba, (size_t)w * h * sizeof(float4), cudaMemcpyHostToDevice, ctx->upload_stream));
+  ctx->textures_pending = true;
   return 0;
 }
 
@@ -418,8 +475,8 @@ int asuna_add_mesh(asuna_ctx* ctx, const AsunaVertex* v, uint32_t nv, const uint
   m.n_vertices = nv, m.n_tris = nt;
   ASUNA_CUDA_CHECK(cudaMalloc(&m.d_vertices, (size_t)nv * sizeof(AsunaVertex)));
   ASUNA_CUDA_CHECK(cudaMalloc(&m.d_indices, (size_t)nt * 3 * sizeof(uint32_t)));
-  ASUNA_CUDA_CHECK(cudaMemcpy(m.d_vertices, v, (size_t)nv * sizeof(AsunaVertex), cudaMemcpyHostToDevice));
-  ASUNA_CUDA_CHECK(cudaMemcpy(m.d_indices, idx, (size_t)nt * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(m.d_vertices, v, (size_t)nv * sizeof(AsunaVertex), cudaMemcpyHostToDevice, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(m.d_indices, idx, (size_t)nt * 3 * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   ctx->meshes.push_back(m);
   ctx->scene_dirty = true;
   return (int)ctx->meshes.size() - 1;
@@ -452,6 +509,7 @@ int asuna_add_instance(asuna_ctx* ctx, const float x[16], uint32_t mesh, uint32_
 }
 
 int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
+  StepTimer tm("build_accel");
   cudaSetDevice(ctx->device);
   if (ctx->instances.empty() || ctx->meshes.empty()) return fail(ctx, ASUNA_E_INVALID, "scene has no instances");
   for (auto& in : ctx->instances)
@@ -520,20 +578,24 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   if (total_tris >= (1u << 27)) return fail(ctx, ASUNA_E_INVALID, "more than 2^27 triangles");
   ctx->pool_nodes = total_nodes, ctx->pool_tris = total_tris;
   ASUNA_CUDA_CHECK(ctx->scratch.reserve(max_prims));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_blas_nodes, total_nodes * sizeof(WideNode)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_build_results, (n_mesh + 2) * sizeof(BuildResult)));
+  {
+    ArenaPlan plan;
+    plan.add(ctx->d_blas_nodes, total_nodes * sizeof(WideNode));
+    plan.add(ctx->d_build_results, (n_mesh + 2) * sizeof(BuildResult));
+    plan.add(ctx->d_tris, total_tris * sizeof(TriSlot));
+    plan.add(ctx->d_tlas_nodes, std::max<uint32_t>(n_tlas - 1, 1) * sizeof(WideNode));
+    plan.add(ctx->d_tlas_leaf_inst, n_tlas * sizeof(uint32_t));
+    plan.add(ctx->d_tlas_ids, n_tlas * sizeof(uint32_t));
+    plan.add(ctx->d_instances, (n_inst + 1) * sizeof(DInstance));
+    plan.add(ctx->d_meshes, n_mesh * sizeof(DMesh));
+    plan.add(ctx->d_mesh_lo, (n_mesh + 1) * sizeof(float4));
+    plan.add(ctx->d_mesh_hi, (n_mesh + 1) * sizeof(float4));
+    plan.add(ctx->d_materials, std::max<size_t>(ctx->materials.size(), 1) * sizeof(AsunaMaterial));
+    plan.add(ctx->d_lights, std::max<size_t>(ctx->lights.size(), 1) * sizeof(AsunaLight));
+    plan.add(ctx->d_textures, std::max<size_t>(ctx->textures.size(), 1) * sizeof(DTexture));
+    ASUNA_CUDA_CHECK(plan.commit(&ctx->scene_arena));
+  }
   ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->d_build_results, 0, (n_mesh + 2) * sizeof(BuildResult), s));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tris, total_tris * sizeof(TriSlot)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_nodes, std::max<uint32_t>(n_tlas - 1, 1) * sizeof(WideNode)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_leaf_inst, n_tlas * sizeof(uint32_t)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_tlas_ids, n_tlas * sizeof(uint32_t)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_instances, (n_inst + 1) * sizeof(DInstance)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_meshes, n_mesh * sizeof(DMesh)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_mesh_lo, (n_mesh + 1) * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_mesh_hi, (n_mesh + 1) * sizeof(float4)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_materials, std::max<size_t>(ctx->materials.size(), 1) * sizeof(AsunaMaterial)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_lights, std::max<size_t>(ctx->lights.size(), 1) * sizeof(AsunaLight)));
-  ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_textures, std::max<size_t>(ctx->textures.size(), 1) * sizeof(DTexture)));
   TriSlot* d_soup = nullptr;  // world-space triangles in input order; the emit kernel copies them into leaf order
   if (have_world) ASUNA_CUDA_CHECK(cudaMalloc(&d_soup, (size_t)world_tris * sizeof(TriSlot)));
 
@@ -569,7 +631,9 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
     ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_lights, ctx->lights.data(), ctx->lights.size() * sizeof(AsunaLight), cudaMemcpyHostToDevice, s));
   if (!htex.empty())
     ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_textures, htex.data(), htex.size() * sizeof(DTexture), cudaMemcpyHostToDevice, s));
+  tm.step("allocation + table upload enqueue");
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));  // host vectors go out of scope below; also excludes H2D from build time
+  tm.step("wait for uploads");
 
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -613,8 +677,10 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
                                        ctx->d_build_results + n_mesh + 1));
   }
   cudaEventRecord(e1, s);
+  tm.step("build enqueue");
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
   ASUNA_CUDA_CHECK(cudaGetLastError());
+  tm.step("build on the device");
   float ms = 0.f;
   cudaEventElapsedTime(&ms, e0, e1);
   cudaEventDestroy(e0);
@@ -667,7 +733,14 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
         (m.type == ASUNA_MAT_KANG18 && (m.opacityTextureId >= 0 || m.metalness > 0.f)) ||
         (m.type == ASUNA_MAT_DISNEY && (m.opacityTextureId >= 0 || m.rhoSpec[0] > 0.f)))
       ctx->may_pass_through = true;
+  // texture / env-table copies ran on the upload stream while the BVH was being built; rendering waits for them
+  if (ctx->textures_pending) {
+    ASUNA_CUDA_CHECK(cudaEventRecord(ctx->ev_textures, ctx->upload_stream));
+    ASUNA_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_textures, 0));
+    ctx->textures_pending = false;
+  }
   ctx->scene_dirty = false;
+  tm.step("statistics read-back, frees");
   return 0;
 }
 
@@ -838,17 +911,33 @@ int asuna_host_free(asuna_ctx* ctx, void* p) {
 int asuna_export_partial(asuna_ctx* ctx, void** out) {
   if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
   cudaSetDevice(ctx->device);
+  // Stream-ordered: the buffer is complete once the work queued on asuna_stream_handle so far has run.  A collective
+  // issued on ANOTHER stream must wait for that stream (an event, torch's wait_stream); no host sync is needed here.
   launch_export_partial(ctx->stream, ctx->out, ctx->d_partial, ctx->W * ctx->H, ctx->have_accum ? 1 : 0);
-  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ASUNA_CUDA_CHECK(cudaGetLastError());
   *out = ctx->d_partial;
   return 0;
 }
 int asuna_import_partial(asuna_ctx* ctx) {
   if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
   cudaSetDevice(ctx->device);
-  launch_import_partial(ctx->stream, ctx->out, ctx->d_partial, ctx->W * ctx->H);
-  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  launch_import_partial(ctx->stream, ctx->out, ctx->d_partial, ctx->W * ctx->H);  // stream-ordered, like the export
+  ASUNA_CUDA_CHECK(cudaGetLastError());
   ctx->have_accum = true;
+  return 0;
+}
+int asuna_post_process(asuna_ctx* ctx, const AsunaPost* tm, float* out) {
+  if (!tm || !out) return fail(ctx, ASUNA_E_INVALID, "null argument");
+  if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
+  if (tm->tmType >= ASUNA_TM_NUM) return fail(ctx, ASUNA_E_INVALID, "unknown tone mapper");
+  if (tm->tmType == ASUNA_TM_CUSTOM && (tm->autoExposure & 2))
+    return fail(ctx, ASUNA_E_UNSUPPORTED, "local auto-exposure (autoExposure bit 1) reads the display image's mip chain and is not available offline");
+  cudaSetDevice(ctx->device);
+  launch_post_process(ctx->stream, ctx->out.img[0], ctx->d_ldr, ctx->W, ctx->H, *tm, ctx->d_post_sums);
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(out, ctx->d_ldr, (size_t)ctx->W * ctx->H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+  ASUNA_CUDA_CHECK(cudaGetLastError());
+  collect_timers(ctx);
   return 0;
 }
 int asuna_channel_device_ptr(asuna_ctx* ctx, int ch, void** out) {

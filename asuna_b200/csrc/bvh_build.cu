@@ -756,10 +756,8 @@ inline uint32_t div_up(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
 // ------------------------------------------------------------------------------------------------
 BuildScratch::~BuildScratch() { release(); }
 void BuildScratch::release() {
-  void* ptrs[] = {blo, bhi, keys[0], keys[1], vals[0], vals[1], hist, children, nlo, nhi, cost, dec, cid[0], cid[1],
-                  clo[0], clo[1], chi[0], chi[1], nn, pre, block_sums, root_of, counters, bounds};
-  for (void* p : ptrs)
-    if (p) cudaFree(p);
+  if (arena) cudaFree(arena);
+  arena = nullptr;
   blo = bhi = nlo = nhi = nullptr;
   keys[0] = keys[1] = nullptr;
   vals[0] = vals[1] = nullptr;
@@ -786,8 +784,15 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
   if (n <= capacity) return cudaSuccess;
   release();
   uint32_t cap = std::max<uint32_t>(n, 1024);
-#define A(ptr, bytes)                                   \
-  if ((e = cudaMalloc((void**)&ptr, (bytes))) != cudaSuccess) return e;
+  // two passes over the same list: sizes first, then one cudaMalloc and the pointers into it
+  char* base = nullptr;
+  for (int pass = 0; pass < 2; pass++) {
+    size_t off = 0;
+#define A(ptr, bytes)                                                                   \
+  {                                                                                     \
+    if (pass) ptr = reinterpret_cast<std::remove_reference_t<decltype(ptr)>>(base + off);                       \
+    off += (((size_t)(bytes)) + 255) & ~(size_t)255;                                    \
+  }
   A(blo, sizeof(float4) * cap);
   A(bhi, sizeof(float4) * cap);
   A(keys[0], sizeof(uint64_t) * cap);
@@ -811,6 +816,11 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
   A(root_of, sizeof(int) * cap);
   A(counters, sizeof(uint32_t) * 4);
   A(bounds, sizeof(int) * 8);
+    if (!pass) {
+      if ((e = cudaMalloc((void**)&base, off)) != cudaSuccess) return e;
+      arena = base;
+    }
+  }
 #undef A
   capacity = cap;
   return cudaSuccess;

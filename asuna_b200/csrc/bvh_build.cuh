@@ -23,6 +23,7 @@ struct BuildScratch {
   int* root_of = nullptr;                  // binary subtree root of each wide node
   uint32_t* counters = nullptr;
   int* bounds = nullptr;                   // ordered-int centroid bounds (6 words)
+  void* arena = nullptr;                   // all of the above live in ONE device allocation (a build pays one cudaMalloc)
   uint32_t capacity = 0;
   uint32_t coop_blocks = 0;                // co-resident grid size for the cooperative kernels
   ~BuildScratch();

@@ -449,6 +449,112 @@ __global__ void k_import_partial(OutputImages out, const float4* partial, uint32
   out.img[8][i] = make_float4(s.w, s.w, s.w, s.w);
 }
 
+// ---- post-process: src/shaders/post.idle.frag:71-133 + utils/tonemapping.glsl, one thread per pixel -------------------
+namespace post {
+ADEV float3 pow3(float3 c, float e) { return f3(powf(c.x, e), powf(c.y, e), powf(c.z, e)); }
+ADEV float3 linear_to_srgb(float3 c) { return pow3(c, 1.0f / 2.2f); }  // tonemapping.glsl:27-33 (INV_GAMMA = 1 / 2.2)
+ADEV float3 srgb_to_linear(float3 c) { return pow3(c, 2.2f); }
+ADEV float3 uncharted2(float3 c) {  // :43-54
+  const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+  return ((c * (A * c + C * B) + D * E) / (c * (A * c + B) + D * F)) - E / F;
+}
+ADEV float3 tone_map_uncharted(float3 c) {  // :56-61
+  c = uncharted2(c * 2.0f);
+  const float3 white = f3(1.0f) / uncharted2(f3(11.2f));
+  return linear_to_srgb(c * white);
+}
+ADEV float3 hejl_richard(float3 c) {  // :65-68
+  c = f3(fmaxf(0.0f, c.x - 0.004f), fmaxf(0.0f, c.y - 0.004f), fmaxf(0.0f, c.z - 0.004f));
+  return (c * (6.2f * c + 0.5f)) / (c * (6.2f * c + 1.7f) + 0.06f);
+}
+ADEV float3 aces(float3 c) {  // :73-81
+  const float A = 2.51f, B = 0.03f, C = 2.43f, D = 0.59f, E = 0.14f;
+  float3 v = (c * (A * c + B)) / (c * (C * c + D) + E);
+  return linear_to_srgb(f3(fminf(fmaxf(v.x, 0.0f), 1.0f), fminf(fmaxf(v.y, 0.0f), 1.0f), fminf(fmaxf(v.z, 0.0f), 1.0f)));
+}
+ADEV float pbrt_channel(float x) { return x < 0.0031308f ? 12.92f * x : 1.055f * powf(x, 1.0f / 2.4f) - 0.055f; }
+ADEV float mixf(float a, float b, float t) { return a * (1.0f - t) + b * t; }
+}  // namespace post
+
+// mean of the radiance image (the 1x1 mip level textureLod(inImage, 0.5, 20) reads, post.idle.frag:104-105): fixed-shape
+// two-level sum, so the result does not depend on scheduling
+__global__ void __launch_bounds__(256) k_image_sum(const float4* __restrict__ img, uint32_t n, double* __restrict__ block_sums) {
+  __shared__ double sh[3][8];
+  double s[3] = {0.0, 0.0, 0.0};
+  for (uint32_t i = blockIdx.x * 256 + threadIdx.x; i < n; i += gridDim.x * 256) {
+    float4 v = img[i];
+    s[0] += v.x, s[1] += v.y, s[2] += v.z;
+  }
+  for (int c = 0; c < 3; c++) {
+    for (int o = 16; o > 0; o >>= 1) s[c] += __shfl_xor_sync(0xFFFFFFFFu, s[c], o);
+    if ((threadIdx.x & 31) == 0) sh[c][threadIdx.x >> 5] = s[c];
+  }
+  __syncthreads();
+  if (threadIdx.x < 3) {
+    double t = 0.0;
+    for (int w = 0; w < 8; w++) t += sh[threadIdx.x][w];
+    block_sums[blockIdx.x * 3 + threadIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_post_process(const float4* __restrict__ hdr_img, float4* __restrict__ ldr, uint32_t w,
+                                                      uint32_t h, AsunaPost tm, const double* __restrict__ block_sums,
+                                                      uint32_t n_sum_blocks) {
+  using namespace post;
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  const uint32_t x = i % w, y = i / w;
+  const float4 in = hdr_img[i];
+  float3 hdr = f3(in.x, in.y, in.z), out;
+  switch (tm.tmType) {
+    case ASUNA_TM_NONE: out = hdr; break;
+    case ASUNA_TM_GAMMA: out = linear_to_srgb(hdr / (f3(1.0f) + hdr / 1.5f)); break;
+    case ASUNA_TM_REINHARD: out = hejl_richard(hdr); break;  // post.idle.frag:80-81 maps "Reinhard" to Hejl-Richard
+    case ASUNA_TM_ACES: out = aces(hdr); break;
+    case ASUNA_TM_FILMIC: out = hejl_richard(hdr); break;     // :85-87, the same curve spelled out
+    case ASUNA_TM_PBRT: out = f3(pbrt_channel(hdr.x), pbrt_channel(hdr.y), pbrt_channel(hdr.z)); break;
+    default: {  // ASUNA_TM_CUSTOM, :101-132
+      float3 c = hdr;
+      if (tm.autoExposure & 1) {  // toneExposure, :39-44
+        double sr = 0.0, sg = 0.0, sb = 0.0;
+        for (uint32_t b = 0; b < n_sum_blocks; b++) sr += block_sums[3 * b], sg += block_sums[3 * b + 1], sb += block_sums[3 * b + 2];
+        const double inv = 1.0 / ((double)w * (double)h);
+        const float avg_lum = 0.2126f * (float)(sr * inv) + 0.7152f * (float)(sg * inv) + 0.0722f * (float)(sb * inv);
+        const float Yxyz = 0.3575761f * c.x + 0.7151522f * c.y + 0.1191920f * c.z;  // row y of RGB2XYZ as GLSL builds it (column-major constructor)
+        const float Y = (tm.key / avg_lum) * Yxyz;
+        const float Yd = (Y * (1.0f + Y / (tm.Ywhite * tm.Ywhite))) / (1.0f + Y);
+        c = c / Yxyz * Yd;
+      }
+      c = tone_map_uncharted(c * tm.avgLum);  // toneMap(), TONEMAP_UNCHARTED is defined at post.idle.frag:17
+      // dithering, :22-27 with pcg3d noise (utils/random.glsl:74-84)
+      uint32_t vx = x * 1664525u + 1013904223u, vy = y * 1664525u + 1013904223u, vz = 1013904223u;
+      vx += vy * vz, vy += vz * vx, vz += vx * vy;
+      vx ^= vx >> 16, vy ^= vy >> 16, vz ^= vz >> 16;
+      vx += vy * vz, vy += vz * vx, vz += vx * vy;
+      const float3 noise = f3(__uint_as_float(0x3f800000u | (vx >> 9)) - 1.0f, __uint_as_float(0x3f800000u | (vy >> 9)) - 1.0f,
+                              __uint_as_float(0x3f800000u | (vz >> 9)) - 1.0f);
+      const float quant = 1.0f / 255.0f;
+      const float3 lin = srgb_to_linear(c), s = linear_to_srgb(lin);
+      const float3 c0 = f3(floorf(s.x / quant) * quant, floorf(s.y / quant) * quant, floorf(s.z / quant) * quant);
+      const float3 c1 = c0 + f3(quant);
+      const float3 l0 = srgb_to_linear(c0), l1 = srgb_to_linear(c1);
+      const float3 discr = f3(mixf(l0.x, l1.x, noise.x), mixf(l0.y, l1.y, noise.y), mixf(l0.z, l1.z, noise.z));
+      c = f3(discr.x < lin.x ? c1.x : c0.x, discr.y < lin.y ? c1.y : c0.y, discr.z < lin.z ? c1.z : c0.z);
+      // contrast, brightness, saturation, vignette
+      c = f3(fminf(fmaxf(mixf(0.5f, c.x, tm.contrast), 0.0f), 1.0f), fminf(fmaxf(mixf(0.5f, c.y, tm.contrast), 0.0f), 1.0f),
+             fminf(fmaxf(mixf(0.5f, c.z, tm.contrast), 0.0f), 1.0f));
+      c = pow3(c, 1.0f / tm.brightness);
+      const float g = 0.299f * c.x + 0.587f * c.y + 0.114f * c.z;
+      c = f3(mixf(g, c.x, tm.saturation), mixf(g, c.y, tm.saturation), mixf(g, c.z, tm.saturation));
+      const float ux = ((((float)x + 0.5f) / (float)w) * tm.renderingRatio[0] - 0.5f) * 2.0f;
+      const float uy = ((((float)y + 0.5f) / (float)h) * tm.renderingRatio[1] - 0.5f) * 2.0f;
+      c = c * (1.0f - (ux * ux + uy * uy) * tm.vignette);
+      out = c;
+    }
+  }
+  ldr[i] = make_float4(out.x, out.y, out.z, in.w);
+}
+
 __global__ void k_primary_rays(const __grid_constant__ FrameParams fp, float4* rays) {
   uint32_t pixel = blockIdx.x * blockDim.x + threadIdx.x;
   if (pixel >= fp.n_pixels) return;
@@ -533,6 +639,11 @@ void launch_export_partial(cudaStream_t s, const OutputImages& out, float4* part
 }
 void launch_import_partial(cudaStream_t s, const OutputImages& out, const float4* partial, uint32_t n) {
   k_import_partial<<<div_up(n, 256), 256, 0, s>>>(out, partial, n);
+}
+void launch_post_process(cudaStream_t s, const float4* hdr, float4* ldr, uint32_t w, uint32_t h, const AsunaPost& tm, double* block_sums) {
+  const uint32_t n = w * h, sum_blocks = 296;
+  if (tm.tmType == ASUNA_TM_CUSTOM && (tm.autoExposure & 1)) k_image_sum<<<sum_blocks, 256, 0, s>>>(hdr, n, block_sums);
+  k_post_process<<<div_up(n, 256), 256, 0, s>>>(hdr, ldr, w, h, tm, block_sums, sum_blocks);
 }
 void launch_primary_rays(cudaStream_t s, const FrameParams& fp, float4* rays) {
   k_primary_rays<<<div_up(fp.n_pixels, 256), 256, 0, s>>>(fp, rays);

@@ -28,6 +28,8 @@ void launch_trace_shadow(cudaStream_t s, const LaunchDims& ld, const SceneView& 
 void launch_accumulate(cudaStream_t s, const FrameParams& fp, const PathState& ps, const OutputImages& out);
 void launch_export_partial(cudaStream_t s, const OutputImages& out, float4* partial, uint32_t n, int have_accum);
 void launch_import_partial(cudaStream_t s, const OutputImages& out, const float4* partial, uint32_t n);
+// block_sums: 3 x 296 doubles of scratch (only touched for the custom tone mapper with auto-exposure)
+void launch_post_process(cudaStream_t s, const float4* hdr, float4* ldr, uint32_t w, uint32_t h, const AsunaPost& tm, double* block_sums);
 void launch_primary_rays(cudaStream_t s, const FrameParams& fp, float4* rays);
 void launch_trace_user(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const float4* rays, uint32_t n, float* tuv,
                        uint32_t* inst_prim, uint8_t* occluded, Counters* cnt);

@@ -45,6 +45,23 @@ Stats = np.dtype([
     ("node_visits", np.uint64), ("tri_tests", np.uint64), ("trace_ms", f4), ("shade_ms", f4), ("total_ms", f4),
     ("build_ms", f4), ("closest_ms", f4), ("shadow_ms", f4), ("pad", f4, 2)])
 
+# GpuPushConstantPost, reference src/shared/pushconstant.h:49-62
+Post = np.dtype([("brightness", f4), ("contrast", f4), ("saturation", f4), ("vignette", f4), ("avgLum", f4), ("zoom", f4),
+                 ("renderingRatio", f4, 2), ("autoExposure", np.int32), ("Ywhite", f4), ("key", f4), ("tmType", np.uint32)])
+assert Post.itemsize == 48
+TONE_MAPPERS = {"none": 0, "gamma": 1, "reinhard": 2, "Aces": 3, "filmic": 4, "pbrt": 5, "custom": 6}  # loader.cpp:205-222
+
+
+def default_post(tone_mapping="filmic"):
+    """reference src/core/state.h:46-58"""
+    p = np.zeros((), Post)
+    p["brightness"] = p["contrast"] = p["saturation"] = p["avgLum"] = p["zoom"] = 1.0
+    p["renderingRatio"] = (1.0, 1.0)
+    p["Ywhite"] = p["key"] = 0.5
+    p["tmType"] = TONE_MAPPERS[tone_mapping]
+    return p
+
+
 EXPECTED_SIZES = (44, 132, 76, 224, 84, 96)
 assert (Vertex.itemsize, Material.itemsize, Light.itemsize, Camera.itemsize, State.itemsize,
         SunSky.itemsize) == EXPECTED_SIZES

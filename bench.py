@@ -247,9 +247,14 @@ def main():
         """Multi-GPU combine: one NCCL reduce of the (sum w*L, sum w) plane to rank 0, then L = sum/w."""
         if world == 1:
             return
+        # no host synchronisation: export / import are ordered on the library's stream, the reduce on torch's; each
+        # side waits for the other through stream events (wait_stream)
         t = torch.as_tensor(_Ptr(ctx.export_partial(), n_px * 4), device=dev)
+        lib_stream = torch.cuda.ExternalStream(ctx.stream_handle(), device=dev)
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_stream(lib_stream)
         dist.reduce(t, dst=0, op=dist.ReduceOp.SUM)
-        torch.cuda.synchronize()
+        lib_stream.wait_stream(cur)
         if rank == 0:
             ctx.import_partial()
 
@@ -365,12 +370,12 @@ def main():
         ctx.set_partition(rank, world)
         t2 = time.perf_counter()
         sc.begin_shot(ctx, 0)
-        ctx.render_frames(args.tti_spp)
+        ctx.render_frames(args.tti_spp)  # asynchronous: the launches are queued, the host goes on
+        img = ctx.pinned_image() if rank == 0 else None  # page-locked read-back buffer, allocated while the GPU renders
         ctx.sync()
         t3 = time.perf_counter()
         resolve()
         if rank == 0:
-            img = ctx.pinned_image()
             ctx.read_channel(0, out=img)
         t4 = time.perf_counter()
         barrier()

@@ -30,6 +30,8 @@ std::string exe_dir() {
 }
 }  // namespace
 
+// Host-side tone mappers for the image-conversion hook (main.cpp --convert) only; rendered shots are tone-mapped on the
+// device by asuna_post_process.
 void tonemap(const std::string& name, int n, const float* hdr, float* out) {
   auto to_srgb = [](float c) { return std::pow(c, 1.0f / 2.2f); };  // linearTosRGB, utils/tonemapping.glsl:30-33
   for (int i = 0; i < n; i++) {
@@ -100,6 +102,31 @@ void Tracer::init() {
   }
 }
 
+namespace {
+// One host thread per GPU: asuna_render_frames enqueues a whole shot (and, for opacity pass-through scenes, waits on
+// the device between bounces), so driving N contexts from one thread would serialise the GPUs.
+template <class F>
+void for_each_gpu(int n, F&& fn) {
+  if (n == 1) {
+    fn(0);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::vector<std::string> err((size_t)n);
+  for (int g = 0; g < n; g++)
+    th.emplace_back([&, g] {
+      try {
+        fn(g);
+      } catch (const std::exception& e) {
+        err[(size_t)g] = e.what();
+      }
+    });
+  for (auto& t : th) t.join();
+  for (auto& e : err)
+    if (!e.empty()) throw std::runtime_error(e);
+}
+}  // namespace
+
 std::vector<ShotReport> Tracer::run() {
   std::vector<ShotReport> reports;
   const int n = (int)m_ctx.size();
@@ -110,11 +137,11 @@ std::vector<ShotReport> Tracer::run() {
       const int cnt = (int)std::min<size_t>((size_t)n, m_scene.shots.size() - first);
       double t0 = now_ms();
       std::vector<int> tot(cnt, 0);
-      for (int g = 0; g < cnt; g++) {
+      for_each_gpu(cnt, [&](int g) {
         tot[g] = m_scene.begin_shot(m_ctx[g], first + (size_t)g);
         check(m_ctx[g], asuna_render_frames(m_ctx[g], (uint32_t)tot[g]), "asuna_render_frames");
-      }
-      for (int g = 0; g < cnt; g++) check(m_ctx[g], asuna_sync(m_ctx[g]), "asuna_sync");
+        check(m_ctx[g], asuna_sync(m_ctx[g]), "asuna_sync");
+      });
       double render_ms = now_ms() - t0;
       for (int g = 0; g < cnt; g++) {
         ShotReport rep;
@@ -133,28 +160,32 @@ std::vector<ShotReport> Tracer::run() {
     ShotReport rep;
     rep.shot = (int)shot;
     double t0 = now_ms();
-    int tot = 0;
-    for (int g = 0; g < n; g++) tot = m_scene.begin_shot(m_ctx[g], shot);
-    rep.spp = tot;
-    // every context walks all `tot` frames and renders the ones its partition owns
-    for (int g = 0; g < n; g++) check(m_ctx[g], asuna_render_frames(m_ctx[g], (uint32_t)tot), "asuna_render_frames");
-    for (int g = 0; g < n; g++) check(m_ctx[g], asuna_sync(m_ctx[g]), "asuna_sync");
-    if (n > 1) {
-      size_t count = (size_t)m_scene.camera.width * m_scene.camera.height * 4;
-      std::vector<void*> part(n), stream(n);
-      for (int g = 0; g < n; g++) {
-        check(m_ctx[g], asuna_export_partial(m_ctx[g], &part[g]), "asuna_export_partial");
-        check(m_ctx[g], asuna_stream_handle(m_ctx[g], &stream[g]), "asuna_stream_handle");
+    std::vector<int> tots((size_t)n, 0);
+    std::vector<void*> part((size_t)n, nullptr), stream((size_t)n, nullptr);
+    // every context walks all `tot` frames and renders the ones its partition owns; the partial sums are exported in
+    // stream order right behind the last frame (no host synchronisation anywhere before the read-back)
+    for_each_gpu(n, [&](int g) {
+      tots[(size_t)g] = m_scene.begin_shot(m_ctx[g], shot);
+      check(m_ctx[g], asuna_render_frames(m_ctx[g], (uint32_t)tots[(size_t)g]), "asuna_render_frames");
+      if (n > 1) {
+        check(m_ctx[g], asuna_export_partial(m_ctx[g], &part[(size_t)g]), "asuna_export_partial");
+        check(m_ctx[g], asuna_stream_handle(m_ctx[g], &stream[(size_t)g]), "asuna_stream_handle");
       }
+    });
+    const int tot = tots[0];
+    rep.spp = tot;
+    if (n > 1) {
+      // one NCCL sum to GPU 0 on the contexts' own streams: ordered after the export kernels, before the import kernel
+      size_t count = (size_t)m_scene.camera.width * m_scene.camera.height * 4;
       ncclGroupStart();
       for (int g = 0; g < n; g++) {
         cudaSetDevice(m_tis.gpu_id + g);
-        ncclReduce(part[g], part[g], count, ncclFloat, ncclSum, 0, (ncclComm_t)m_comms[g], (cudaStream_t)stream[g]);
+        ncclReduce(part[(size_t)g], part[(size_t)g], count, ncclFloat, ncclSum, 0, (ncclComm_t)m_comms[(size_t)g], (cudaStream_t)stream[(size_t)g]);
       }
       if (ncclGroupEnd() != ncclSuccess) throw std::runtime_error("ncclReduce failed");
-      for (int g = 0; g < n; g++) check(m_ctx[g], asuna_sync(m_ctx[g]), "asuna_sync");
       check(m_ctx[0], asuna_import_partial(m_ctx[0]), "asuna_import_partial");
     }
+    for (int g = 0; g < n; g++) check(m_ctx[g], asuna_sync(m_ctx[g]), "asuna_sync");
     rep.render_ms = now_ms() - t0;
     double t1 = now_ms();
     save_shot((int)shot);
@@ -191,11 +222,20 @@ void Tracer::save_buffer(const std::string& path_in, int channel_id, int gpu) {
   if (path.empty() || path[0] != '/') path = exe_dir() + path;  // relative paths are taken from the executable's directory
   const int w = m_scene.camera.width, h = m_scene.camera.height;
   std::vector<float> data((size_t)w * h * 4);
-  check(m_ctx[gpu], asuna_read_channel(m_ctx[gpu], channel_id < 0 ? 0 : channel_id, data.data()), "asuna_read_channel");
-  if (channel_id < 0) {  // the post-processed colour: tone mapping of the raw radiance (no denoiser on this path)
-    std::vector<float> ldr(data.size());
-    tonemap(m_scene.output.tone_mapping, w * h, data.data(), ldr.data());
-    data.swap(ldr);
+  if (channel_id < 0) {
+    // the post-processed colour: PipelinePost on the device (asuna_post_process, all seven tone mappers of
+    // post.idle.frag; no denoiser on this path).  Defaults of the post state: src/core/state.h:46-58.
+    static const char* names[] = {"none", "gamma", "reinhard", "Aces", "filmic", "pbrt", "custom"};
+    AsunaPost post{};
+    post.brightness = post.contrast = post.saturation = post.avgLum = post.zoom = 1.0f;
+    post.renderingRatio[0] = post.renderingRatio[1] = 1.0f;
+    post.Ywhite = post.key = 0.5f;
+    post.tmType = ASUNA_TM_NONE;  // loader.cpp:206-225: an unknown name falls back to none
+    for (uint32_t k = 0; k < ASUNA_TM_NUM; k++)
+      if (m_scene.output.tone_mapping == names[k]) post.tmType = k;
+    check(m_ctx[gpu], asuna_post_process(m_ctx[gpu], &post, data.data()), "asuna_post_process");
+  } else {
+    check(m_ctx[gpu], asuna_read_channel(m_ctx[gpu], channel_id, data.data()), "asuna_read_channel");
   }
   if (m_tis.output_f32) write_npy_f32(path + ".npy", {(size_t)h, (size_t)w, 4}, data.data());
   if (!m_tis.output_scanline || channel_id == 0 || channel_id == -1) {

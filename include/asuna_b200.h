@@ -169,6 +169,20 @@ enum AsunaError {
   ASUNA_E_UNSUPPORTED = -4 /* material type outside the hot-path scope */
 };
 
+/* GpuPushConstantPost, reference src/shared/pushconstant.h:49-62 (48 bytes): the post-process / tone-mapping state.
+ * Defaults: reference src/core/state.h:46-58 (everything 1 / 0, Ywhite = key = 0.5, tmType Filmic). */
+typedef struct AsunaPost {
+  float brightness, contrast, saturation, vignette, avgLum, zoom;
+  float renderingRatio[2];
+  int32_t autoExposure; /* bit 0: global exposure from the image mean; bit 1: local (mip-chain) exposure -- unsupported */
+  float Ywhite, key;
+  uint32_t tmType; /* AsunaToneMapping */
+} AsunaPost;
+typedef enum AsunaToneMapping { /* reference src/shared/pushconstant.h:36-46 */
+  ASUNA_TM_NONE = 0, ASUNA_TM_GAMMA = 1, ASUNA_TM_REINHARD = 2, ASUNA_TM_ACES = 3, ASUNA_TM_FILMIC = 4,
+  ASUNA_TM_PBRT = 5, ASUNA_TM_CUSTOM = 6, ASUNA_TM_NUM = 7
+} AsunaToneMapping;
+
 /* Counters a caller may read after a render; all are totals since the last asuna_reset_stats.
  * Times are device times from CUDA events recorded on the context's stream around each launch, kept only while
  * asuna_set_profiling is on (build_ms is always measured). */
@@ -260,9 +274,18 @@ int asuna_host_free(asuna_ctx* ctx, void* host_ptr);
 /* Multi-GPU combine.  export: writes (sum_w*L.rgb, sum_w) per pixel into a device buffer
  * owned by the library and returns its device pointer (w*h*4 floats) for the caller's
  * reduce (NCCL sum).  import: reads that buffer back after the reduce and stores
- * L = sum_wL / sum_w into image 0 and sum_w into image 8. */
+ * L = sum_wL / sum_w into image 0 and sum_w into image 8.
+ * Both are ordered on the context's stream (asuna_stream_handle) and do not synchronise the host: a collective issued on
+ * that stream needs nothing else; one issued on another stream must wait for it and be waited for (events /
+ * wait_stream), or bracket the call with asuna_sync. */
 int asuna_export_partial(asuna_ctx* ctx, void** out_device_ptr);
 int asuna_import_partial(asuna_ctx* ctx);
+
+/* ≙ PipelinePost::run (reference src/pipeline/pipeline_post.cpp:24-43, src/shaders/post.idle.frag:71-133) followed by
+ * the read of the offline colour image (src/tracer/tracer.cpp:236-255, 358-359): tone-maps radiance image 0 on the
+ * device with all seven tone mappers of the reference (custom: Uncharted-2 curve, dithering, contrast / brightness /
+ * saturation / vignette, optional global auto-exposure) and returns w*h RGBA32F in host memory. */
+int asuna_post_process(asuna_ctx* ctx, const AsunaPost* tm, float* rgba32f_out);
 
 /* Device pointer of output image `channel` (w*h float4), for zero-copy consumers. */
 int asuna_channel_device_ptr(asuna_ctx* ctx, int channel, void** out_device_ptr);

@@ -1778,6 +1778,84 @@ int oracle_read_channel(oracle_ctx* c, int ch, float* out) {
   std::memcpy(out, c->images[ch].data(), c->images[ch].size() * sizeof(float));
   return 0;
 }
+// post.idle.frag:71-133 + utils/tonemapping.glsl over image 0 (≙ asuna_post_process).  In libref.so the fragment shader
+// itself runs (refglsl_post_process).
+int oracle_post_process(oracle_ctx* c, const AsunaPost* tm, float* out) {
+  if (!tm || !out || c->W == 0 || tm->tmType >= ASUNA_TM_NUM) return ASUNA_E_INVALID;
+  if (tm->tmType == ASUNA_TM_CUSTOM && (tm->autoExposure & 2)) return ASUNA_E_UNSUPPORTED;
+#ifdef ASUNA_REF_SHADERS
+  refglsl_post_process(c->images[0].data(), c->W, c->H, tm, out);
+#else
+  const size_t n = (size_t)c->W * c->H;
+  auto srgb = [](vec3 v) { return pow3(v, 1.0f / 2.2f); };
+  auto lin = [](vec3 v) { return pow3(v, 2.2f); };
+  auto unch = [](vec3 v) {
+    const float A = 0.15f, B = 0.50f, C = 0.10f, D = 0.20f, E = 0.02f, F = 0.30f;
+    return ((v * (A * v + C * B) + D * E) / (v * (A * v + B) + D * F)) - E / F;
+  };
+  auto hejl = [](vec3 v) {
+    v = vec3(std::fmax(0.0f, v.x - 0.004f), std::fmax(0.0f, v.y - 0.004f), std::fmax(0.0f, v.z - 0.004f));
+    return (v * (6.2f * v + 0.5f)) / (v * (6.2f * v + 1.7f) + 0.06f);
+  };
+  auto pbrt = [](float x) { return x < 0.0031308f ? 12.92f * x : 1.055f * std::pow(x, 1.0f / 2.4f) - 0.055f; };
+  float avg_lum = 1.0f;
+  if (tm->tmType == ASUNA_TM_CUSTOM && (tm->autoExposure & 1)) {
+    double s[3] = {0, 0, 0};
+    for (size_t i = 0; i < n; i++)
+      for (int k = 0; k < 3; k++) s[k] += c->images[0][4 * i + k];
+    avg_lum = 0.2126f * (float)(s[0] / n) + 0.7152f * (float)(s[1] / n) + 0.0722f * (float)(s[2] / n);
+  }
+  for (size_t i = 0; i < n; i++) {
+    const float* in = &c->images[0][4 * i];
+    const uint32_t x = (uint32_t)(i % c->W), y = (uint32_t)(i / c->W);
+    vec3 hdr(in[0], in[1], in[2]), o;
+    switch (tm->tmType) {
+      case ASUNA_TM_NONE: o = hdr; break;
+      case ASUNA_TM_GAMMA: o = srgb(hdr / (hdr / 1.5f + 1.0f)); break;
+      case ASUNA_TM_REINHARD:
+      case ASUNA_TM_FILMIC: o = hejl(hdr); break;
+      case ASUNA_TM_ACES: {
+        vec3 v = (hdr * (2.51f * hdr + 0.03f)) / (hdr * (2.43f * hdr + 0.59f) + 0.14f);
+        o = srgb(clamp3(v, 0.0f, 1.0f));
+        break;
+      }
+      case ASUNA_TM_PBRT: o = vec3(pbrt(hdr.x), pbrt(hdr.y), pbrt(hdr.z)); break;
+      default: {
+        vec3 v = hdr;
+        if (tm->autoExposure & 1) {
+          const float Yxyz = 0.3575761f * v.x + 0.7151522f * v.y + 0.1191920f * v.z;
+          const float Y = (tm->key / avg_lum) * Yxyz;
+          const float Yd = (Y * (1.0f + Y / (tm->Ywhite * tm->Ywhite))) / (1.0f + Y);
+          v = v / Yxyz * Yd;
+        }
+        v = unch(v * tm->avgLum * 2.0f);
+        v = srgb(v * (vec3(1.0f) / unch(vec3(11.2f))));
+        uint32_t vx = x * 1664525u + 1013904223u, vy = y * 1664525u + 1013904223u, vz = 1013904223u;
+        vx += vy * vz, vy += vz * vx, vz += vx * vy;
+        vx ^= vx >> 16, vy ^= vy >> 16, vz ^= vz >> 16;
+        vx += vy * vz, vy += vz * vx, vz += vx * vy;
+        auto u2f = [](uint32_t r) { return intBitsToFloat((int32_t)(0x3f800000u | (r >> 9))) - 1.0f; };
+        const vec3 noise(u2f(vx), u2f(vy), u2f(vz));
+        const float q = 1.0f / 255.0f;
+        const vec3 l = lin(v), sg = srgb(l);
+        const vec3 c0(std::floor(sg.x / q) * q, std::floor(sg.y / q) * q, std::floor(sg.z / q) * q), c1 = c0 + q;
+        const vec3 l0 = lin(c0), l1 = lin(c1);
+        const vec3 d(mixf(l0.x, l1.x, noise.x), mixf(l0.y, l1.y, noise.y), mixf(l0.z, l1.z, noise.z));
+        v = vec3(d.x < l.x ? c1.x : c0.x, d.y < l.y ? c1.y : c0.y, d.z < l.z ? c1.z : c0.z);
+        v = clamp3(vec3(mixf(0.5f, v.x, tm->contrast), mixf(0.5f, v.y, tm->contrast), mixf(0.5f, v.z, tm->contrast)), 0.0f, 1.0f);
+        v = pow3(v, 1.0f / tm->brightness);
+        const float g = 0.299f * v.x + 0.587f * v.y + 0.114f * v.z;
+        v = vec3(mixf(g, v.x, tm->saturation), mixf(g, v.y, tm->saturation), mixf(g, v.z, tm->saturation));
+        const float ux = ((((float)x + 0.5f) / (float)c->W) * tm->renderingRatio[0] - 0.5f) * 2.0f;
+        const float uy = ((((float)y + 0.5f) / (float)c->H) * tm->renderingRatio[1] - 0.5f) * 2.0f;
+        o = v * (1.0f - (ux * ux + uy * uy) * tm->vignette);
+      }
+    }
+    out[4 * i] = o.x, out[4 * i + 1] = o.y, out[4 * i + 2] = o.z, out[4 * i + 3] = in[3];
+  }
+#endif
+  return 0;
+}
 int oracle_export_partial(oracle_ctx* c, void** out) {
   size_t n = (size_t)c->W * c->H;
   c->partial.resize(n * 4);

@@ -68,7 +68,7 @@ def rewrite(src, name):
     # GLSL evaluates function arguments left to right; C++ leaves the order open (g++ goes right to left)
     # except inside braces.  The only calls with two side-effecting arguments are rand2 / rand3
     # (utils/math.glsl:43-44); everything else is checked to have at most one RNG draw per statement.
-    src = re.sub(r"\bvec([23])\((rand\(seed\)(?:, rand\(seed\))+)\)", r"vec\1{\2}", src)
+    src = re.sub(r"\bvec([23])\((rand\((\w+)\)(?:, rand\(\3\))+)\)", r"vec\1{\2}", src)
     for stmt in src.split(";"):
         body = stmt.split("{")[-1]
         if len(re.findall(r"\b(?:rand[23]?|pcg)\s*\(", body)) > 1 and "vec2{" not in stmt and "vec3{" not in stmt:
@@ -95,6 +95,16 @@ def generate(ref):
     parts.append("namespace rmiss_shadow {\n" + rewrite(rd(sh, "raytrace.shadow.rmiss"), "src/shaders/raytrace.shadow.rmiss") + "}\n")
     parts.append(inc("shim_trace.inc"))
     parts.append("namespace rgen {\n" + rewrite(rd(sh, "raytrace.projective.rgen"), "src/shaders/raytrace.projective.rgen") + "}\n")
+    # post-process stage (LDR output): post.idle.frag with its own copies of tonemapping.glsl (it defines
+    # TONEMAP_UNCHARTED before the include) and random.glsl
+    post = rd(sh, "post.idle.frag")
+    post = re.sub(r"(\w+)\.rgb\s*=([^;]*);", r"assign_rgb(\1, \2);", strip_comments(post))  # lvalue swizzles
+    post = re.sub(r"=\s*float\[\d+\]\(([^;]*)\);", r"= {\1};", post)                       # GLSL array constructor
+    tm = rd(sh, "utils", "tonemapping.glsl").replace("TONEMAPPING_GLSL", "TONEMAPPING_GLSL_POST")
+    parts.append("namespace post_idle {\n" + inc("shim_post.inc") + "#define TONEMAP_UNCHARTED\n" +
+                 rewrite(tm, "src/shaders/utils/tonemapping.glsl (post)") +
+                 rewrite(rd(sh, "utils", "random.glsl"), "src/shaders/utils/random.glsl") +
+                 rewrite(post.replace("#define TONEMAP_UNCHARTED", ""), "src/shaders/post.idle.frag") + "}\n")
     parts.append(inc("shim_export.inc"))
     parts.append(inc("shim_hooks.inc") if os.path.exists(os.path.join(HERE, "shim_hooks.inc")) else "")
     parts.append("}  // namespace refglsl\n")

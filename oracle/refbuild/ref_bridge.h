@@ -68,6 +68,10 @@ typedef struct ShadeProbe {
 // hit == NULL runs raytrace.default.rmiss, otherwise the hit group of the instance.
 void refglsl_shade_probe(const RefHit* hit, ShadeProbe* p);
 
+
+// raytrace post stage: post.idle.frag over a w x h RGBA32F image; tm = GpuPushConstantPost (48 B)
+void refglsl_post_process(const float* hdr, uint32_t w, uint32_t h, const void* tm48, float* out);
+
 #ifdef __cplusplus
 }
 #endif

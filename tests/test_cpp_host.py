@@ -195,6 +195,17 @@ def test_hdr_exr_pfm_round_trips(cli, tmp_path):
     assert np.array_equal(got[..., :3], f[..., :3].astype(np.float16).astype(np.float32)) and np.all(got[..., 3] == 1)
     head = open(str(tmp_path / "f.exr"), "rb").read(4)
     assert head == bytes([0x76, 0x2F, 0x31, 0x01])
+    # an independent OpenEXR implementation (the one inside OpenCV) reads our file, and ours reads its file
+    os.environ["OPENCV_IO_ENABLE_OPENEXR"] = "1"
+    ext = cv2.imread(str(tmp_path / "f.exr"), cv2.IMREAD_UNCHANGED)
+    if ext is not None:  # OpenCV builds without OpenEXR return None
+        assert ext.dtype == np.float32 and np.array_equal(ext[..., ::-1], f[..., :3].astype(np.float16).astype(np.float32))
+        for flags in ([cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_HALF], [cv2.IMWRITE_EXR_TYPE, cv2.IMWRITE_EXR_TYPE_FLOAT]):
+            if cv2.imwrite(str(tmp_path / "cv.exr"), np.ascontiguousarray(f[..., 2::-1]), flags):
+                _convert(cli, str(tmp_path / "cv.exr"), str(tmp_path / "cv_exr.npy"))
+                back = np.load(str(tmp_path / "cv_exr.npy"))[..., :3]
+                want = f[..., :3].astype(np.float16).astype(np.float32) if flags[1] == cv2.IMWRITE_EXR_TYPE_HALF else f[..., :3]
+                assert np.array_equal(back, want)
     _convert(cli, str(tmp_path / "f.npy"), str(tmp_path / "f.pfm"))
     _convert(cli, str(tmp_path / "f.pfm"), str(tmp_path / "f_pfm.npy"))
     assert np.array_equal(np.load(str(tmp_path / "f_pfm.npy"))[..., :3], f[..., :3])

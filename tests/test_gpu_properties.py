@@ -58,6 +58,7 @@ def test_full_size_partition_invariance(full_scene, product_lib):
         assert ctx.stats()["paths"] == 4 * 1920 * 1080
         import torch
         ptr = ctx.export_partial()
+        ctx.sync()  # the export is stream-ordered on the library's stream; torch below uses its own
         parts.append((ctx, ptr))
     import torch
     # stand-in for ncclReduce(sum) to rank 0: add rank 1's partial plane into rank 0's, on the device

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from conftest import GOLDEN
-from asuna_b200 import metrics, scenes
+from asuna_b200 import metrics, scenes, structs as S
 from test_gpu_parity import SCENES, silhouette_mask
 
 pytestmark = pytest.mark.gpu
@@ -120,3 +120,30 @@ def test_opacity_pass_through_scene(gpu_ctx, ref_ctx):
         elif int(m["type"]) == 1:
             m["metalness"] = 0.35
     check(sc, gpu_ctx, ref_ctx)
+
+
+def test_post_process_on_gpu_vs_reference_glsl(gpu_ctx, ref_ctx):
+    """asuna_post_process (k_post_process) against post.idle.frag compiled as C++ (or the restatement pinned to it), all
+    seven tone mappers incl. the custom one with grading and global auto-exposure.  The CPU side tone-maps the GPU's own
+    HDR image, so only the post stage is compared."""
+    from test_ref_pins import post_agreement, post_cases
+    sc = scenes.cornell_materials(96, 72, spp=4, env=True, lights="rect", textured=True)
+    sc.upload(gpu_ctx), sc.upload(ref_ctx)
+    hdr = sc.render_shot(gpu_ctx, 0)[0]
+    sc.render_shot(ref_ctx, 0, spp=1)
+    # hand the GPU's radiance image to the CPU path: export/import round trip of (L * 1, 1)
+    import ctypes as C
+    ptr = C.cast(ref_ctx.export_partial(), C.POINTER(C.c_float))
+    part = np.ctypeslib.as_array(ptr, shape=hdr.shape)
+    part[..., :3], part[..., 3] = hdr[..., :3], 1.0
+    ref_ctx.import_partial()
+    assert np.array_equal(ref_ctx.read_channel(0)[..., :3], hdr[..., :3])
+    for name, tm in post_cases():
+        g, c = gpu_ctx.post_process(tm), ref_ctx.post_process(tm)
+        frac, worst = post_agreement(g, c)
+        custom = name.startswith("custom")
+        assert frac <= (0.01 if custom else 0.0) and worst <= (1.5 / 255 if custom else 2e-5), (name, frac, worst)
+    bad = S.default_post("custom")
+    bad["autoExposure"] = 3
+    with pytest.raises(Exception):
+        gpu_ctx.post_process(bad)

@@ -485,6 +485,41 @@ def test_partitioned_accumulation_matches_reference_glsl(ref_lib):
     assert np.abs(s[..., :3] / s[..., 3:4] - W[..., :3]).max() <= 2e-5
 
 
+def post_cases():
+    """(name, GpuPushConstantPost) for all seven tone mappers (post.idle.frag:76-133), the custom one also with
+    non-default grading and with global auto-exposure."""
+    cases = [(n, S.default_post(n)) for n in S.TONE_MAPPERS]
+    p = S.default_post("custom")
+    p["contrast"], p["brightness"], p["saturation"], p["vignette"], p["avgLum"] = 1.2, 0.9, 0.7, 0.3, 1.4
+    cases.append(("custom_graded", p))
+    p = S.default_post("custom")
+    p["autoExposure"], p["key"], p["Ywhite"] = 1, 0.4, 0.8
+    cases.append(("custom_auto_exposure", p))
+    return cases
+
+
+def post_agreement(a, b):
+    """Tone-mapped images: fp32 pow() chains agree to ~1e-6; the custom mapper's dither picks one of two 8-bit levels by
+    a `<` on values an ulp apart, so a small fraction of channels may sit one quantisation step (1/255) away."""
+    d = np.abs(a[..., :3].astype(np.float64) - b[..., :3])
+    return float((d > 2e-5).mean()), float(d.max())
+
+
+def test_post_process_oracle_vs_reference_glsl(cpu_ctx, ref_ctx):
+    """PipelinePost: post.idle.frag compiled as C++ against the restatement (the one asuna_post_process is tested against
+    on the GPU), every tone mapper, on a rendered HDR image with values from 0 to the clamp at 10."""
+    sc = scenes.cornell_materials(64, 48, spp=4, env=True, lights="rect", textured=True)
+    sc.upload(cpu_ctx), sc.upload(ref_ctx)
+    A, B = sc.render_shot(cpu_ctx, 0)[0], sc.render_shot(ref_ctx, 0)[0]
+    assert np.abs(A - B).max() < 0.2  # same picture (a few branch-flipped pixels aside)
+    for name, tm in post_cases():
+        a, b = cpu_ctx.post_process(tm), ref_ctx.post_process(tm)
+        same_input = np.abs(A - B).max(axis=2) <= 1e-6
+        frac, worst = post_agreement(a[same_input], b[same_input])
+        assert frac <= (0.01 if name.startswith("custom") else 0.0) and worst <= (1.5 / 255 if name.startswith("custom") else 2e-5), (name, frac, worst)
+        assert np.array_equal(a[..., 3], A[..., 3])
+
+
 # ----------------------------------------------------------------------------- frozen vectors (always run)
 def _golden(name):
     p = os.path.join(GOLDEN, name)
