@@ -19,6 +19,26 @@
 
 using namespace asuna;
 
+// ASUNA_TIMING=1: host-side wall time of the steps of asuna_create / asuna_build_accel on stderr (developer probe for
+// the serial part of a job, tools/upload_probe.py)
+static double wall_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+struct StepTimer {
+  bool on = getenv("ASUNA_TIMING") != nullptr;
+  double t = wall_ms();
+  const char* what;
+  explicit StepTimer(const char* w) : what(w) {}
+  void step(const char* name) {
+    if (!on) return;
+    double n = wall_ms();
+    fprintf(stderr, "[asuna timing] %s: %s %.3f ms\n", what, name, n - t);
+    t = n;
+  }
+};
+
 namespace {
 struct NvtxRange {  // one named range per pipeline stage (tracing / profiling hooks)
   explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
@@ -238,6 +258,7 @@ void free_path_buffers(asuna_ctx* ctx) {
 
 int ensure_path_buffers(asuna_ctx* ctx, uint32_t n_paths) {
   if (n_paths <= ctx->path_capacity) return 0;
+  StepTimer tm("path state");
   free_path_buffers(ctx);
   size_t n = n_paths;
   ArenaPlan plan;
@@ -249,6 +270,7 @@ int ensure_path_buffers(asuna_ctx* ctx, uint32_t n_paths) {
   plan.add(ctx->ps.kind, n), plan.add(ctx->ps.sorted, n * sizeof(uint32_t));
   plan.add(ctx->ps.bin_hist, ((n + kBinTile - 1) / kBinTile) * kNumKinds * sizeof(uint32_t));
   ASUNA_CUDA_CHECK(plan.commit(&ctx->path_arena));
+  tm.step("allocation");
   ctx->path_capacity = n_paths;
   return 0;
 }
@@ -317,26 +339,6 @@ void asuna_abi_sizes(uint32_t out[6]) {
   out[0] = sizeof(AsunaVertex), out[1] = sizeof(AsunaMaterial), out[2] = sizeof(AsunaLight);
   out[3] = sizeof(AsunaCamera), out[4] = sizeof(AsunaState), out[5] = sizeof(AsunaSunSky);
 }
-
-// ASUNA_TIMING=1: host-side wall time of the steps of asuna_create / asuna_build_accel on stderr (developer probe for
-// the serial part of a job, tools/upload_probe.py)
-static double wall_ms() {
-  timespec ts;
-  clock_gettime(CLOCK_MONOTONIC, &ts);
-  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
-}
-struct StepTimer {
-  bool on = getenv("ASUNA_TIMING") != nullptr;
-  double t = wall_ms();
-  const char* what;
-  explicit StepTimer(const char* w) : what(w) {}
-  void step(const char* name) {
-    if (!on) return;
-    double n = wall_ms();
-    fprintf(stderr, "[asuna timing] %s: %s %.3f ms\n", what, name, n - t);
-    t = n;
-  }
-};
 
 int asuna_create(asuna_ctx** out, int gpu_id) {
   *out = nullptr;
@@ -420,6 +422,7 @@ int asuna_set_film(asuna_ctx* ctx, uint32_t w, uint32_t h) {
   cudaSetDevice(ctx->device);
   ctx->W = w, ctx->H = h;
   size_t bytes = (size_t)w * h * sizeof(float4);
+  StepTimer tm("set_film");
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   free_dev(ctx->film_arena);
   ArenaPlan plan;
@@ -429,19 +432,23 @@ int asuna_set_film(asuna_ctx* ctx, uint32_t w, uint32_t h) {
   plan.add(ctx->d_post_sums, 3 * 296 * sizeof(double));
   ASUNA_CUDA_CHECK(plan.commit(&ctx->film_arena));
   ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->film_arena, 0, ((bytes + 255) & ~(size_t)255) * ASUNA_NUM_OUTPUT_IMAGES, ctx->stream));
+  tm.step("allocation + clear enqueue");
   ctx->have_accum = false;
   return 0;
 }
 
 static int upload_texture(asuna_ctx* ctx, HostTexture& t, const float* rgba, uint32_t w, uint32_t h) {
+  StepTimer tm("texture");
   free_dev(t.d_texels);
   t.w = w, t.h = h;
   ASUNA_CUDA_CHECK(cudaMalloc(&t.d_texels, (size_t)w * h * sizeof(float4)));
+  tm.step("allocation");
   // On the upload stream: the call returns once the host buffer has been consumed (pageable memory is staged by the
   // driver, so the pointer may be reused at once), the DMA itself overlaps whatever the caller does next -- usually
   // asuna_build_accel.  Rendering waits for ev_textures.
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(t.d_texels, rgba, (size_t)w * h * sizeof(float4), cudaMemcpyHostToDevice, ctx->upload_stream));
   ctx->textures_pending = true;
+  if (w * h > 65536) tm.step("copy (host side)");
   return 0;
 }
 
@@ -604,7 +611,13 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
   }
   ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->d_build_results, 0, (n_mesh + 2) * sizeof(BuildResult), s));
   TriSlot* d_soup = nullptr;  // world-space triangles in input order; the emit kernel copies them into leaf order
-  if (have_world) ASUNA_CUDA_CHECK(cudaMalloc(&d_soup, (size_t)world_tris * sizeof(TriSlot)));
+  WorldJob* d_jobs = nullptr;
+  if (have_world) {
+    // one temporary allocation: the soup and, behind it, the per-instance job table of k_world_triangles_batched
+    const size_t soup_bytes = ((size_t)world_tris * sizeof(TriSlot) + 255) & ~(size_t)255;
+    ASUNA_CUDA_CHECK(cudaMalloc(&d_soup, soup_bytes + merged.size() * sizeof(WorldJob)));
+    d_jobs = reinterpret_cast<WorldJob*>(reinterpret_cast<char*>(d_soup) + soup_bytes);
+  }
 
   // flat tables
   std::vector<DInstance> hinst(n_inst + 1);
@@ -661,13 +674,17 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
     ASUNA_CUDA_CHECK(launch_build_wide(s, m.n_tris, ctx->d_blas_nodes, (uint32_t)m.node_base, (uint32_t)m.tri_base, ctx->scratch,
                                        pl, cost_prim, ctx->d_mesh_lo + i, ctx->d_mesh_hi + i, ctx->d_build_results + i));
   }
-  if (have_world) {  // the world BLAS over the single-use instances
-    uint32_t off = 0;
+  std::vector<WorldJob> jobs;  // must outlive the enqueued copy: the stream is synchronised before this function returns
+  if (have_world) {  // the world BLAS over the flattened instances: every instance's triangles to world space, one launch
+    uint32_t off = 0, max_n = 0;
     for (uint32_t i : merged) {
       const HostMesh& m = ctx->meshes[ctx->instances[i].mesh];
-      launch_world_triangles(s, m.d_vertices, m.d_indices, m.n_tris, hinst[i].o2w, i, d_soup, off, off == 0, ctx->scratch);
+      jobs.push_back(WorldJob{m.d_vertices, m.d_indices, hinst[i].o2w[0], hinst[i].o2w[1], hinst[i].o2w[2], m.n_tris, off, i, 0u});
       off += m.n_tris;
+      max_n = std::max(max_n, m.n_tris);
     }
+    ASUNA_CUDA_CHECK(cudaMemcpyAsync(d_jobs, jobs.data(), jobs.size() * sizeof(WorldJob), cudaMemcpyHostToDevice, s));
+    launch_world_triangles_batched(s, d_jobs, (uint32_t)jobs.size(), max_n, d_soup, ctx->scratch);
     PrimPayload pl;
     pl.soup = d_soup, pl.tris = ctx->d_tris;
     ASUNA_CUDA_CHECK(launch_build_wide(s, world_tris, ctx->d_blas_nodes, (uint32_t)world_node_base, (uint32_t)world_tri_base,

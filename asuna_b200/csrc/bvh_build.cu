@@ -16,6 +16,7 @@
 
 #include <algorithm>
 #include <cfloat>
+#include <cstdlib>
 
 #include "bvh_build.cuh"
 #include "scan.cuh"
@@ -56,13 +57,19 @@ __device__ __forceinline__ void reduce_bounds(float3 lo, float3 hi, bool valid, 
     mxy = fmaxf(mxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o));
     mxz = fmaxf(mxz, __shfl_xor_sync(0xFFFFFFFFu, mxz, o));
   }
+  // One atomic per warp only where it would still move the bound: six same-line atomics from every one of the million
+  // warps of a 32 M-triangle build serialise in one L2 slice (measured: 4.6 ms of a 28 ms build); the plain read is cheap
+  // and after the first few thousand warps almost nothing improves the bounds any more.
   if ((threadIdx.x & 31) == 0) {
-    atomicMin(&bounds[0], float_to_ordered(mnx));
-    atomicMin(&bounds[1], float_to_ordered(mny));
-    atomicMin(&bounds[2], float_to_ordered(mnz));
-    atomicMax(&bounds[3], float_to_ordered(mxx));
-    atomicMax(&bounds[4], float_to_ordered(mxy));
-    atomicMax(&bounds[5], float_to_ordered(mxz));
+    const volatile int* b = bounds;
+    const int o0 = float_to_ordered(mnx), o1 = float_to_ordered(mny), o2 = float_to_ordered(mnz);
+    const int o3 = float_to_ordered(mxx), o4 = float_to_ordered(mxy), o5 = float_to_ordered(mxz);
+    if (o0 < b[0]) atomicMin(&bounds[0], o0);
+    if (o1 < b[1]) atomicMin(&bounds[1], o1);
+    if (o2 < b[2]) atomicMin(&bounds[2], o2);
+    if (o3 > b[3]) atomicMax(&bounds[3], o3);
+    if (o4 > b[4]) atomicMax(&bounds[4], o4);
+    if (o5 > b[5]) atomicMax(&bounds[5], o5);
   }
 }
 
@@ -111,6 +118,34 @@ __global__ void k_world_triangles(const AsunaVertex* __restrict__ v, const uint3
                      fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
     blo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
     bhi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
+  }
+  reduce_bounds(lo, hi, valid, bounds);
+}
+
+// The same for many instances in ONE launch (blockIdx.y = job): a scene of 100 instances used to pay 100 launches of
+// ~1300 blocks each, every one with its own ramp-up and tail.
+__global__ void __launch_bounds__(kThreads) k_world_triangles_batched(const WorldJob* __restrict__ jobs, TriSlot* __restrict__ soup,
+                                                                      float4* __restrict__ blo, float4* __restrict__ bhi, int* bounds) {
+  const WorldJob job = jobs[blockIdx.y];
+  if (blockIdx.x * kThreads >= job.n) return;  // whole block idle: no barrier or ballot is skipped by part of a warp
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool valid = i < job.n;
+  float3 lo = make_float3(0, 0, 0), hi = lo;
+  if (valid) {
+    const AsunaVertex* v = job.v;
+    const uint32_t* idx = job.idx;
+    TriSlot t;
+    t.v0 = world_vertex(v[idx[3 * (size_t)i + 0]].pos, job.r0, job.r1, job.r2, __uint_as_float(i));
+    t.v1 = world_vertex(v[idx[3 * (size_t)i + 1]].pos, job.r0, job.r1, job.r2, __uint_as_float(job.inst));
+    t.v2 = world_vertex(v[idx[3 * (size_t)i + 2]].pos, job.r0, job.r1, job.r2, 0.f);
+    const size_t o = (size_t)job.offset + i;
+    soup[o] = t;
+    lo = make_float3(fminf(t.v0.x, fminf(t.v1.x, t.v2.x)), fminf(t.v0.y, fminf(t.v1.y, t.v2.y)),
+                     fminf(t.v0.z, fminf(t.v1.z, t.v2.z)));
+    hi = make_float3(fmaxf(t.v0.x, fmaxf(t.v1.x, t.v2.x)), fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)),
+                     fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
+    blo[o] = make_float4(lo.x, lo.y, lo.z, 0.f);
+    bhi[o] = make_float4(hi.x, hi.y, hi.z, 0.f);
   }
   reduce_bounds(lo, hi, valid, bounds);
 }
@@ -306,6 +341,13 @@ __global__ void __launch_bounds__(kThreads) k_sort_scatter(const uint64_t* __res
 #define ASUNA_PLOC_RADIUS 10
 #endif
 constexpr int kPlocRadius = ASUNA_PLOC_RADIUS;
+#ifndef ASUNA_PLOC_TAIL
+#define ASUNA_PLOC_TAIL 4096
+#endif
+constexpr int kPlocTail = ASUNA_PLOC_TAIL;
+#ifndef ASUNA_PLOC_MIN_BLOCKS
+#define ASUNA_PLOC_MIN_BLOCKS 4  // 64 registers: 32 resident warps per SM instead of 24 at the natural 75
+#endif  // clusters left when one block takes over (see k_ploc)
 constexpr uint64_t kDecLeaf = 1ull;
 
 struct PlocParams {
@@ -397,7 +439,7 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t& total,
   return before + s - v;
 }
 
-__global__ void __launch_bounds__(kThreads) k_ploc(const PlocParams a) {
+__global__ void __launch_bounds__(kThreads, ASUNA_PLOC_MIN_BLOCKS) k_ploc(const PlocParams a) {
   cg::grid_group grid = cg::this_grid();
   __shared__ uint32_t warp_sums[kThreads / 32];
   __shared__ uint32_t red[4];
@@ -421,12 +463,22 @@ __global__ void __launch_bounds__(kThreads) k_ploc(const PlocParams a) {
   }
   grid.sync();
   int m = n, cur = 0, next_inner = n - 2;
+  // Tail: once few clusters are left an iteration is pure synchronisation latency (3 grid-wide barriers for a handful of
+  // merges, and half of all iterations happen below a few thousand clusters), so block 0 finishes alone behind
+  // __syncthreads and the other blocks leave.  nb / bid / the strides describe whichever grid is still running.
+  bool tail = false;
+  uint32_t nb = gridDim.x, bid = blockIdx.x, tid = gtid, tsize = gsize;
   while (m > 1) {
+    if (!tail && m <= kPlocTail) {
+      if (blockIdx.x != 0) return;
+      tail = true;
+      nb = 1, bid = 0, tid = threadIdx.x, tsize = kThreads;
+    }
     const int* cid = a.cid[cur];
     const float4* clo = a.clo[cur];
     const float4* chi = a.chi[cur];
     // phase 1: nearest neighbour inside the radius (ties -> lowest index, so a mutual pair always exists)
-    for (uint32_t i = gtid; i < (uint32_t)m; i += gsize) {
+    for (uint32_t i = tid; i < (uint32_t)m; i += tsize) {
       float4 lo = clo[i], hi = chi[i];
       int j0 = max(0, (int)i - kPlocRadius), j1 = min(m - 1, (int)i + kPlocRadius);
       float best = FLT_MAX;
@@ -438,10 +490,10 @@ __global__ void __launch_bounds__(kThreads) k_ploc(const PlocParams a) {
       }
       a.nn[i] = bj;
     }
-    grid.sync();
+    if (tail) __syncthreads(); else grid.sync();
     // phase 2: survivor / merge flags, prefix inside this block's contiguous chunk (keeps Morton order)
-    const int chunk = (m + (int)gridDim.x - 1) / (int)gridDim.x;
-    const int c0 = min(m, (int)blockIdx.x * chunk), c1 = min(m, c0 + chunk);
+    const int chunk = (m + (int)nb - 1) / (int)nb;
+    const int c0 = min(m, (int)bid * chunk), c1 = min(m, c0 + chunk);
     uint32_t run_valid = 0, run_lead = 0;
     for (int base = c0; base < c1; base += kThreads) {
       int i = base + (int)threadIdx.x;
@@ -457,15 +509,15 @@ __global__ void __launch_bounds__(kThreads) k_ploc(const PlocParams a) {
       run_valid += total & 0xFFFFu;
       run_lead += total >> 16;
     }
-    if (threadIdx.x == 0) a.block_sums[blockIdx.x] = make_uint2(run_valid, run_lead);
-    grid.sync();
+    if (threadIdx.x == 0) a.block_sums[bid] = make_uint2(run_valid, run_lead);
+    if (tail) __syncthreads(); else grid.sync();
     // phase 3: global offsets from the block sums, then merge / copy into the next cluster array
     {
       uint32_t bv = 0, bl = 0, tv = 0, tl = 0;
-      for (uint32_t b = threadIdx.x; b < gridDim.x; b += kThreads) {
+      for (uint32_t b = threadIdx.x; b < nb; b += kThreads) {
         uint2 s = a.block_sums[b];
         tv += s.x, tl += s.y;
-        if (b < blockIdx.x) bv += s.x, bl += s.y;
+        if (b < bid) bv += s.x, bl += s.y;
       }
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -514,7 +566,7 @@ __global__ void __launch_bounds__(kThreads) k_ploc(const PlocParams a) {
       oclo[pos] = lo;
       ochi[pos] = hi;
     }
-    grid.sync();
+    if (tail) __syncthreads(); else grid.sync();
     m = (int)tot_valid;
     next_inner -= (int)tot_lead;
     cur ^= 1;
@@ -569,13 +621,16 @@ __device__ void emit_prim(const EmitParams& a, uint32_t slot, uint32_t prim) {
   }
 }
 
-__device__ void emit_wide_node(const EmitParams& a, uint32_t w) {
+// Called by whole warps (`valid` = this lane has a node): node and primitive-slot ranges are handed out with ONE atomic
+// per warp per counter -- a 1.3 M-triangle build emits 200 k wide nodes, and 400 k same-address atomics cost more than
+// all the arithmetic of this kernel.
+__device__ void emit_wide_node(const EmitParams& a, uint32_t w, bool valid) {
   const int n = a.n;
-  const int root = a.root_of[w];
+  const int root = valid ? a.root_of[w] : 0;
   int ch_node[8];
   bool ch_leaf[8];
   int nc = 0;
-  {
+  if (valid) {
     uint64_t droot = a.dec[root];
     if (root >= n - 1 || (droot & kDecLeaf)) {
       ch_node[0] = root, ch_leaf[0] = true, nc = 1;  // a BVH of <= 3 primitives: one leaf child
@@ -600,7 +655,8 @@ __device__ void emit_wide_node(const EmitParams& a, uint32_t w) {
       }
     }
   }
-  float4 rlo = a.nlo[root], rhi = a.nhi[root];
+  float4 rlo = make_float4(0.f, 0.f, 0.f, 0.f), rhi = rlo;
+  if (valid) rlo = a.nlo[root], rhi = a.nhi[root];
   float4 clo[8], chi[8];
   for (int i = 0; i < nc; i++) clo[i] = a.nlo[ch_node[i]], chi[i] = a.nhi[ch_node[i]];
 
@@ -639,8 +695,25 @@ __device__ void emit_wide_node(const EmitParams& a, uint32_t w) {
     if (ch_leaf[i]) n_prims += __float_as_uint(clo[i].w);
     else n_inner++;
   }
-  uint32_t cb = n_inner ? atomicAdd(&a.counters[0], n_inner) : 0u;
-  uint32_t pb = n_prims ? atomicAdd(&a.counters[1], n_prims) : 0u;
+  uint32_t cb, pb;
+  {
+    const uint32_t lane = threadIdx.x & 31u;
+    uint32_t xi = n_inner, xp = n_prims;  // inclusive warp scans (both are 0 on lanes without a node)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t ti = __shfl_up_sync(0xFFFFFFFFu, xi, o), tp = __shfl_up_sync(0xFFFFFFFFu, xp, o);
+      if (lane >= (uint32_t)o) xi += ti, xp += tp;
+    }
+    const uint32_t tot_i = __shfl_sync(0xFFFFFFFFu, xi, 31), tot_p = __shfl_sync(0xFFFFFFFFu, xp, 31);
+    uint32_t bi = 0, bp = 0;
+    if (lane == 0) {
+      if (tot_i) bi = atomicAdd(&a.counters[0], tot_i);
+      if (tot_p) bp = atomicAdd(&a.counters[1], tot_p);
+    }
+    cb = __shfl_sync(0xFFFFFFFFu, bi, 0) + xi - n_inner;
+    pb = __shfl_sync(0xFFFFFFFFu, bp, 0) + xp - n_prims;
+  }
+  if (!valid) return;
 
   // quantisation grid: origin = padded lower corner, per-axis power-of-two scale covering the padded extent
   float pad[3], p[3], inv_scale[3];
@@ -730,7 +803,10 @@ __global__ void __launch_bounds__(kThreads) k_emit_wide(const EmitParams a) {
   grid.sync();
   uint32_t begin = 0, end = 1;
   while (begin < end) {
-    for (uint32_t w = begin + gtid; w < end; w += gsize) emit_wide_node(a, w);
+    for (uint32_t w0 = begin + (gtid & ~31u); w0 < end; w0 += gsize) {  // whole warps enter together
+      const uint32_t w = w0 + (threadIdx.x & 31u);
+      emit_wide_node(a, w, w < end);
+    }
     grid.sync();
     begin = end;
     end = *(volatile uint32_t*)&a.counters[0];
@@ -779,7 +855,12 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_ploc, kThreads, 0)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_emit_wide, kThreads, 0)) != cudaSuccess) return e;
-    coop_blocks = (uint32_t)(sms * std::max(1, std::min(std::min(per_sm_a, per_sm_b), 4)));
+    // each cooperative kernel gets the largest co-resident grid IT fits: both walk trees through dependent, scattered
+    // loads, so resident warps are what hides their latency (ASUNA_BUILD_BLOCKS_PER_SM caps both, for experiments)
+    int cap_blocks = 8;
+    if (const char* t = getenv("ASUNA_BUILD_BLOCKS_PER_SM")) cap_blocks = std::max(1, atoi(t));
+    coop_blocks = (uint32_t)(sms * std::max(1, std::min(per_sm_a, cap_blocks)));
+    coop_blocks_emit = (uint32_t)(sms * std::max(1, std::min(per_sm_b, cap_blocks)));
   }
   if (n <= capacity) return cudaSuccess;
   release();
@@ -838,6 +919,15 @@ void launch_world_triangles(cudaStream_t s, const AsunaVertex* v, const uint32_t
                                                              sc.blo + offset, sc.bhi + offset, sc.bounds);
 }
 
+void launch_world_triangles_batched(cudaStream_t s, const WorldJob* d_jobs, uint32_t n_jobs, uint32_t max_n, TriSlot* soup,
+                                    BuildScratch& sc) {
+  k_bounds_init<<<1, 32, 0, s>>>(sc.bounds);
+  for (uint32_t j0 = 0; j0 < n_jobs; j0 += 65535u) {  // gridDim.y limit
+    const uint32_t nj = std::min(65535u, n_jobs - j0);
+    k_world_triangles_batched<<<dim3(div_up(max_n, kThreads), nj), kThreads, 0, s>>>(d_jobs + j0, soup, sc.blo, sc.bhi, sc.bounds);
+  }
+}
+
 void launch_instance_boxes(cudaStream_t s, const DInstance* inst, const uint32_t* ids, const float4* mesh_lo,
                            const float4* mesh_hi, uint32_t n, BuildScratch& sc) {
   k_bounds_init<<<1, 32, 0, s>>>(sc.bounds);
@@ -891,7 +981,8 @@ cudaError_t launch_build_wide(cudaStream_t s, uint32_t n, WideNode* nodes, uint3
   ep.soup = payload.soup, ep.prim_ids = payload.prim_ids;
   ep.out_lo = root_lo, ep.out_hi = root_hi, ep.result = result;
   void* eargs[] = {&ep};
-  return cudaLaunchCooperativeKernel((const void*)k_emit_wide, dim3(grid), dim3(kThreads), eargs, 0, s);
+  const uint32_t grid_emit = std::max(1u, std::min(sc.coop_blocks_emit, div_up(n, kThreads)));
+  return cudaLaunchCooperativeKernel((const void*)k_emit_wide, dim3(grid_emit), dim3(kThreads), eargs, 0, s);
 }
 
 // Host-side debug/test hook: sorts (key,value) pairs with the builder's radix sort.

@@ -25,7 +25,8 @@ struct BuildScratch {
   int* bounds = nullptr;                   // ordered-int centroid bounds (6 words)
   void* arena = nullptr;                   // all of the above live in ONE device allocation (a build pays one cudaMalloc)
   uint32_t capacity = 0;
-  uint32_t coop_blocks = 0;                // co-resident grid size for the cooperative kernels
+  uint32_t coop_blocks = 0;                // co-resident grid size of k_ploc ...
+  uint32_t coop_blocks_emit = 0;           // ... and of k_emit_wide
   ~BuildScratch();
   cudaError_t reserve(uint32_t n);
   void release();
@@ -48,6 +49,15 @@ struct BuildResult {  // written by the emit kernel, read back once after all bu
   uint32_t pad;
 };
 
+// One instance of the merged world-space BLAS: `n` triangles of a mesh taken through o2w into soup[offset ...).
+struct WorldJob {
+  const AsunaVertex* v;
+  const uint32_t* idx;
+  float4 r0, r1, r2;  // object -> world rows
+  uint32_t n, offset, inst, pad;
+};
+void launch_world_triangles_batched(cudaStream_t s, const WorldJob* d_jobs, uint32_t n_jobs, uint32_t max_n, TriSlot* soup,
+                                    BuildScratch& sc);
 void launch_tri_boxes(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, BuildScratch& sc);
 void launch_world_triangles(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, const float4 o2w[3],
                             uint32_t inst, TriSlot* soup, uint32_t offset, bool first, BuildScratch& sc);
