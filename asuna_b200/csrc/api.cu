@@ -590,6 +590,7 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
     max_prims = std::max(max_prims, world_tris);
   }
   if (total_tris >= (1u << 27)) return fail(ctx, ASUNA_E_INVALID, "more than 2^27 triangles");
+  if (n_inst >= (1u << 28)) return fail(ctx, ASUNA_E_INVALID, "more than 2^28 instances");
   ctx->pool_nodes = total_nodes, ctx->pool_tris = total_tris;
   ASUNA_CUDA_CHECK(ctx->scratch.reserve(max_prims));
   {
@@ -679,7 +680,8 @@ int asuna_build_accel(asuna_ctx* ctx, float* out_ms) {
     uint32_t off = 0, max_n = 0;
     for (uint32_t i : merged) {
       const HostMesh& m = ctx->meshes[ctx->instances[i].mesh];
-      jobs.push_back(WorldJob{m.d_vertices, m.d_indices, hinst[i].o2w[0], hinst[i].o2w[1], hinst[i].o2w[2], m.n_tris, off, i, 0u});
+      jobs.push_back(WorldJob{m.d_vertices, m.d_indices, hinst[i].o2w[0], hinst[i].o2w[1], hinst[i].o2w[2], m.n_tris, off, i,
+                              hinst[i].mat_type == 0xFFFFFFFFu ? (uint32_t)kKindLight : kKindMaterial0 + hinst[i].mat_type});
       off += m.n_tris;
       max_n = std::max(max_n, m.n_tris);
     }

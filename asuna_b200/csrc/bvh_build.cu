@@ -100,30 +100,8 @@ __device__ __forceinline__ float4 world_vertex(const float* p, float4 r0, float4
                      __fmaf_rn(r1.z, p[2], __fmaf_rn(r1.y, p[1], __fmaf_rn(r1.x, p[0], r1.w))),
                      __fmaf_rn(r2.z, p[2], __fmaf_rn(r2.y, p[1], __fmaf_rn(r2.x, p[0], r2.w))), w);
 }
-__global__ void k_world_triangles(const AsunaVertex* __restrict__ v, const uint32_t* __restrict__ idx, uint32_t n,
-                                  float4 r0, float4 r1, float4 r2, uint32_t inst, TriSlot* __restrict__ soup,
-                                  float4* __restrict__ blo, float4* __restrict__ bhi, int* bounds) {
-  uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  bool valid = i < n;
-  float3 lo = make_float3(0, 0, 0), hi = lo;
-  if (valid) {
-    TriSlot t;
-    t.v0 = world_vertex(v[idx[3 * (size_t)i + 0]].pos, r0, r1, r2, __uint_as_float(i));
-    t.v1 = world_vertex(v[idx[3 * (size_t)i + 1]].pos, r0, r1, r2, __uint_as_float(inst));
-    t.v2 = world_vertex(v[idx[3 * (size_t)i + 2]].pos, r0, r1, r2, 0.f);
-    soup[i] = t;
-    lo = make_float3(fminf(t.v0.x, fminf(t.v1.x, t.v2.x)), fminf(t.v0.y, fminf(t.v1.y, t.v2.y)),
-                     fminf(t.v0.z, fminf(t.v1.z, t.v2.z)));
-    hi = make_float3(fmaxf(t.v0.x, fmaxf(t.v1.x, t.v2.x)), fmaxf(t.v0.y, fmaxf(t.v1.y, t.v2.y)),
-                     fmaxf(t.v0.z, fmaxf(t.v1.z, t.v2.z)));
-    blo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
-    bhi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
-  }
-  reduce_bounds(lo, hi, valid, bounds);
-}
-
-// The same for many instances in ONE launch (blockIdx.y = job): a scene of 100 instances used to pay 100 launches of
-// ~1300 blocks each, every one with its own ramp-up and tail.
+// One launch for all instances (blockIdx.y = job): a scene of 100 instances used to pay 100 launches of ~1300 blocks
+// each, every one with its own ramp-up and tail.
 __global__ void __launch_bounds__(kThreads) k_world_triangles_batched(const WorldJob* __restrict__ jobs, TriSlot* __restrict__ soup,
                                                                       float4* __restrict__ blo, float4* __restrict__ bhi, int* bounds) {
   const WorldJob job = jobs[blockIdx.y];
@@ -136,7 +114,7 @@ __global__ void __launch_bounds__(kThreads) k_world_triangles_batched(const Worl
     const uint32_t* idx = job.idx;
     TriSlot t;
     t.v0 = world_vertex(v[idx[3 * (size_t)i + 0]].pos, job.r0, job.r1, job.r2, __uint_as_float(i));
-    t.v1 = world_vertex(v[idx[3 * (size_t)i + 1]].pos, job.r0, job.r1, job.r2, __uint_as_float(job.inst));
+    t.v1 = world_vertex(v[idx[3 * (size_t)i + 1]].pos, job.r0, job.r1, job.r2, __uint_as_float(job.inst | (job.kind << 28)));
     t.v2 = world_vertex(v[idx[3 * (size_t)i + 2]].pos, job.r0, job.r1, job.r2, 0.f);
     const size_t o = (size_t)job.offset + i;
     soup[o] = t;
@@ -857,7 +835,7 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_emit_wide, kThreads, 0)) != cudaSuccess) return e;
     // each cooperative kernel gets the largest co-resident grid IT fits: both walk trees through dependent, scattered
     // loads, so resident warps are what hides their latency (ASUNA_BUILD_BLOCKS_PER_SM caps both, for experiments)
-    int cap_blocks = 8;
+    int cap_blocks = 4;  // measured on B200: 3 / 4 / 6 / 8 blocks per SM -> 26.9 / 25.5 / 25.9 / 25.8 ms at 32.8 M triangles, 2.15 / 2.11 / 2.18 / 2.18 ms at 1.31 M
     if (const char* t = getenv("ASUNA_BUILD_BLOCKS_PER_SM")) cap_blocks = std::max(1, atoi(t));
     coop_blocks = (uint32_t)(sms * std::max(1, std::min(per_sm_a, cap_blocks)));
     coop_blocks_emit = (uint32_t)(sms * std::max(1, std::min(per_sm_b, cap_blocks)));
@@ -910,13 +888,6 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
 void launch_tri_boxes(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, BuildScratch& sc) {
   k_bounds_init<<<1, 32, 0, s>>>(sc.bounds);
   k_tri_boxes<<<div_up(n, kThreads), kThreads, 0, s>>>(v, idx, n, sc.blo, sc.bhi, sc.bounds);
-}
-
-void launch_world_triangles(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, const float4 o2w[3],
-                            uint32_t inst, TriSlot* soup, uint32_t offset, bool first, BuildScratch& sc) {
-  if (first) k_bounds_init<<<1, 32, 0, s>>>(sc.bounds);
-  k_world_triangles<<<div_up(n, kThreads), kThreads, 0, s>>>(v, idx, n, o2w[0], o2w[1], o2w[2], inst, soup + offset,
-                                                             sc.blo + offset, sc.bhi + offset, sc.bounds);
 }
 
 void launch_world_triangles_batched(cudaStream_t s, const WorldJob* d_jobs, uint32_t n_jobs, uint32_t max_n, TriSlot* soup,

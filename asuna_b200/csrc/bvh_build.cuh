@@ -54,13 +54,12 @@ struct WorldJob {
   const AsunaVertex* v;
   const uint32_t* idx;
   float4 r0, r1, r2;  // object -> world rows
-  uint32_t n, offset, inst, pad;
+  uint32_t n, offset, inst;
+  uint32_t kind;  // HitKind of the instance (emitter / material type): stored above the instance id in the slot's v1.w
 };
 void launch_world_triangles_batched(cudaStream_t s, const WorldJob* d_jobs, uint32_t n_jobs, uint32_t max_n, TriSlot* soup,
                                     BuildScratch& sc);
 void launch_tri_boxes(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, BuildScratch& sc);
-void launch_world_triangles(cudaStream_t s, const AsunaVertex* v, const uint32_t* idx, uint32_t n, const float4 o2w[3],
-                            uint32_t inst, TriSlot* soup, uint32_t offset, bool first, BuildScratch& sc);
 void launch_instance_boxes(cudaStream_t s, const DInstance* inst, const uint32_t* ids, const float4* mesh_lo,
                            const float4* mesh_hi, uint32_t n, BuildScratch& sc);
 cudaError_t launch_build_wide(cudaStream_t s, uint32_t n, WideNode* nodes, uint32_t node_base, uint32_t prim_base,

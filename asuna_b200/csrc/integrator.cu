@@ -42,12 +42,16 @@ struct ClosestPolicy {  // rgen:108-109: tmin 1e-5, tmax 1e10; the hit record go
     tmin = kMinimum, tmax = kInfinity;
     return slot;
   }
-  ADEV void commit(uint32_t i, uint32_t slot, bool, const HitRec& h) const {
+  ADEV void commit(uint32_t i, uint32_t slot, bool, const HitRec& h, uint32_t kind_hint) const {
     ps.hit[slot] = make_uint4(__float_as_uint(h.b1), __float_as_uint(h.b2), h.inst, h.prim);
     uint32_t kind = kKindMiss;  // the key the hit queue is regrouped by before shading
     if (h.inst != 0xFFFFFFFFu) {
-      const uint32_t mt = __ldg(&instances[h.inst].mat_type);
-      kind = mt == 0xFFFFFFFFu ? (uint32_t)kKindLight : kKindMaterial0 + mt;
+      if (kind_hint != kKindUnknown) {
+        kind = kind_hint;  // single-level kernels: came with the triangle slot
+      } else {
+        const uint32_t mt = __ldg(&instances[h.inst].mat_type);
+        kind = mt == 0xFFFFFFFFu ? (uint32_t)kKindLight : kKindMaterial0 + mt;
+      }
     }
     ps.kind[i] = (uint8_t)kind;
   }
@@ -61,7 +65,7 @@ struct ShadowPolicy {  // rgen:117-125: tmin 0, tmax = dist - 2 EPS, first hit e
     tmin = 0.0f, tmax = a.w;
     return 0u;
   }
-  ADEV void commit(uint32_t i, uint32_t, bool occluded, const HitRec&) const {
+  ADEV void commit(uint32_t i, uint32_t, bool occluded, const HitRec&, uint32_t) const {
     if (occluded) return;
     const uint32_t slot = __float_as_uint(ps.sh_d[i].w);
     const float4 L = ps.sh_l[i], r = ps.rad[slot];
@@ -79,7 +83,7 @@ struct UserPolicy {  // asuna_trace_rays / asuna_occlusion_rays / asuna_trace_pr
     o = f3(a), d = f3(b), tmin = a.w, tmax = b.w;
     return 0u;
   }
-  ADEV void commit(uint32_t i, uint32_t, bool found, const HitRec& h) const {
+  ADEV void commit(uint32_t i, uint32_t, bool found, const HitRec& h, uint32_t) const {
     if (occluded) {
       occluded[i] = found ? 1 : 0;
       return;
@@ -94,7 +98,7 @@ __global__ void __launch_bounds__(kTraceThreads, SINGLE ? ASUNA_TRACE_MIN_BLOCKS
 k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter, int qsel) {
   ClosestPolicy pol{ps, ps.queue[qsel], sc.instances};
   constexpr bool kStage = SINGLE && ASUNA_TRACE_STAGE;
-  __shared__ uint32_t stage[kStage ? (kTraceThreads / 32) * kStageWords * 32 : 1];
+  __shared__ __align__(16) uint32_t stage[kStage ? (kTraceThreads / 32) * kStageWords * 32 : 4];
   trace_persistent<false, COUNT, SINGLE, kStage>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow,
                                                  &cnt->node_visits, &cnt->tri_tests, cnt->lane_stats, stage);
 }

@@ -35,6 +35,8 @@ struct HitRec {
   float t, b1, b2;
   uint32_t inst, prim;
 };
+constexpr uint32_t kInstMask = 0x0FFFFFFFu;  // instance id in a world-space triangle slot; the 4 bits above hold the hit kind
+constexpr uint32_t kKindUnknown = 0xFFu;
 
 // Reciprocal for the slab tests only (MUFU.RCP, ~1 ulp): box tests are conservative by half a quantisation step
 // plus 2 ulp, results never depend on it.  The triangle test uses IEEE divisions (bit-exact with the oracle).
@@ -364,9 +366,15 @@ ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
   if (!hit_triangle(L.rs, f3(v0), f3(v1), f3(v2), t, b1, b2)) return false;
   if (!(t > L.tmin)) return false;
   const uint32_t prim = __float_as_uint(v0.w);
-  const uint32_t inst = (SINGLE || L.cur_inst == sc.world_inst) ? __float_as_uint(v1.w) : L.cur_inst;
-  bool closer = t < L.tmax || (t == L.tmax && L.best.inst != 0xFFFFFFFFu &&
-                               (inst < L.best.inst || (inst == L.best.inst && prim < L.best.prim)));
+  // world-space slots carry (hit kind << 28 | instance) in v1.w (k_world_triangles_batched): the single-level kernels keep
+  // the packed word, so that committing a hit needs no look-up of the instance's material type
+  const uint32_t inst = SINGLE ? __float_as_uint(v1.w)
+                               : (L.cur_inst == sc.world_inst ? (__float_as_uint(v1.w) & kInstMask) : L.cur_inst);
+  bool closer = t < L.tmax;
+  if (!closer && t == L.tmax && L.best.inst != 0xFFFFFFFFu) {  // tie: lower (instance, primitive) wins
+    const uint32_t a = SINGLE ? (inst & kInstMask) : inst, b = SINGLE ? (L.best.inst & kInstMask) : L.best.inst;
+    closer = a < b || (a == b && prim < L.best.prim);
+  }
   if (!closer) return false;
   L.best.t = t, L.best.b1 = b1, L.best.b2 = b2, L.best.inst = inst, L.best.prim = prim;
   L.tmax = t;
@@ -384,14 +392,17 @@ ADEV bool lane_triangle_step(Lane& L, const SceneView& sc, uint32_t& n_tris) {
 // kStageWords words) in shared memory.  A lane whose ray finishes starts its prepared ray in the same iteration -- no
 // lane waits for a refill quorum -- and the prepared slots are refilled sc.stage_lanes at a time, so the queue fetch,
 // the global ray loads and the reciprocal / shear set-up run at least that wide.
-constexpr int kStageWords = 19;
+// Slot layout: 20 words per lane, lane-major, moved as five 128-bit shared-memory accesses (the 80-byte lane stride maps
+// the eight lanes of a quarter warp onto disjoint bank quads).  A ray hand-over is executed by one or two lanes at a
+// time in most loop iterations, so its instruction count is paid almost per ray: 5 LDS.128 instead of 19 LDS.32.
+constexpr int kStageWords = 20;
 template <bool ANY, bool COUNT, bool SINGLE, bool STAGE, class Policy>
 __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t count, uint32_t* ticket, uint32_t* overflow,
                                  unsigned long long* node_visits, unsigned long long* tri_tests,
                                  unsigned long long* lane_stats = nullptr, uint32_t* stage_words = nullptr) {
   static_assert(!STAGE || SINGLE, "prepared rays are implemented for the single-level kernels");
   const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u;
-  uint32_t* const stg = STAGE ? stage_words + (threadIdx.x >> 5) * (kStageWords * 32) + lane : nullptr;
+  uint4* const stg = STAGE ? reinterpret_cast<uint4*>(stage_words) + ((threadIdx.x >> 5) * 32 + lane) * (kStageWords / 4) : nullptr;
   bool staged = false;
   Lane L;
   uint2 stack_local[kStackSize + 1];
@@ -412,7 +423,7 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
       float t0, t1;
       const uint32_t g = pol.load(i, o, d, t0, t1);
       lane_begin<SINGLE>(L, sc, o, d, t0, t1);
-      pol.commit(i, g, false, L.best);
+      pol.commit(i, g, false, L.best, kKindUnknown);
     }
     return;
   }
@@ -423,15 +434,15 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
   uint32_t w_next = 0, w_end = 0;
   // start the prepared ray of this lane (STAGE)
   auto take_staged = [&]() {
-    L.rs.o = f3(__uint_as_float(stg[0 * 32]), __uint_as_float(stg[1 * 32]), __uint_as_float(stg[2 * 32]));
-    L.rs.idir = f3(__uint_as_float(stg[3 * 32]), __uint_as_float(stg[4 * 32]), __uint_as_float(stg[5 * 32]));
-    L.rs.sx = f3(__uint_as_float(stg[6 * 32]), __uint_as_float(stg[7 * 32]), __uint_as_float(stg[8 * 32]));
-    L.rs.sy = f3(__uint_as_float(stg[9 * 32]), __uint_as_float(stg[10 * 32]), __uint_as_float(stg[11 * 32]));
-    L.rs.sz = f3(__uint_as_float(stg[12 * 32]), __uint_as_float(stg[13 * 32]), __uint_as_float(stg[14 * 32]));
-    L.rs.oct = (__float_as_uint(L.rs.idir.x) >> 31) | ((__float_as_uint(L.rs.idir.y) >> 31) << 1) |
-               ((__float_as_uint(L.rs.idir.z) >> 31) << 2);
-    L.tmin = __uint_as_float(stg[15 * 32]), L.tmax = __uint_as_float(stg[16 * 32]);
-    ray = stg[17 * 32], tag = stg[18 * 32];
+    const uint4 a = stg[0], b = stg[1], c = stg[2], d = stg[3], e = stg[4];
+    L.rs.o = f3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+    L.rs.idir = f3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+    L.rs.sx = f3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
+    L.rs.sy = f3(__uint_as_float(c.y), __uint_as_float(c.z), __uint_as_float(c.w));
+    L.rs.sz = f3(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z));
+    L.rs.oct = (a.w >> 31) | ((b.x >> 31) << 1) | ((b.y >> 31) << 2);
+    L.tmin = __uint_as_float(d.w), L.tmax = __uint_as_float(e.x);
+    ray = e.y, tag = e.z;
     L.sp = 0;
     L.ng = make_uint2(sc.single_root, 0x80000000u);
     L.tg = make_uint2(0u, 0u);
@@ -463,12 +474,11 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
           RaySpace rs;
           setup_space(rs, o, d);
           setup_shear(rs, d);
-          stg[0 * 32] = __float_as_uint(o.x), stg[1 * 32] = __float_as_uint(o.y), stg[2 * 32] = __float_as_uint(o.z);
-          stg[3 * 32] = __float_as_uint(rs.idir.x), stg[4 * 32] = __float_as_uint(rs.idir.y), stg[5 * 32] = __float_as_uint(rs.idir.z);
-          stg[6 * 32] = __float_as_uint(rs.sx.x), stg[7 * 32] = __float_as_uint(rs.sx.y), stg[8 * 32] = __float_as_uint(rs.sx.z);
-          stg[9 * 32] = __float_as_uint(rs.sy.x), stg[10 * 32] = __float_as_uint(rs.sy.y), stg[11 * 32] = __float_as_uint(rs.sy.z);
-          stg[12 * 32] = __float_as_uint(rs.sz.x), stg[13 * 32] = __float_as_uint(rs.sz.y), stg[14 * 32] = __float_as_uint(rs.sz.z);
-          stg[15 * 32] = __float_as_uint(t0), stg[16 * 32] = __float_as_uint(t1), stg[17 * 32] = i, stg[18 * 32] = g;
+          stg[0] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(rs.idir.x));
+          stg[1] = make_uint4(__float_as_uint(rs.idir.y), __float_as_uint(rs.idir.z), __float_as_uint(rs.sx.x), __float_as_uint(rs.sx.y));
+          stg[2] = make_uint4(__float_as_uint(rs.sx.z), __float_as_uint(rs.sy.x), __float_as_uint(rs.sy.y), __float_as_uint(rs.sy.z));
+          stg[3] = make_uint4(__float_as_uint(rs.sz.x), __float_as_uint(rs.sz.y), __float_as_uint(rs.sz.z), __float_as_uint(t0));
+          stg[4] = make_uint4(__float_as_uint(t1), i, g, 0u);
           staged = true;
         }
       } else if (!active && i < count) {
@@ -497,7 +507,10 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
             setup_space(L.rs, L.wo, L.wd);
           }
           if (L.sp == 0) {
-            pol.commit(ray, tag, L.best.inst != 0xFFFFFFFFu, L.best);
+            const bool found = L.best.inst != 0xFFFFFFFFu;
+            uint32_t kind = kKindUnknown;
+            if (SINGLE && found) kind = L.best.inst >> 28, L.best.inst &= kInstMask;
+            pol.commit(ray, tag, found, L.best, kind);
             active = false;
             if (STAGE && staged) take_staged();
           } else {
@@ -524,7 +537,8 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
         if (m_node == 0u || __popc(m_tri) >= (__popc(m_act) >> sc.tri_vote_shift)) {
           if (COUNT) ls_fired++, ls_tri += __popc(m_tri);
           if (want_tri && lane_triangle_step<ANY, COUNT, SINGLE>(L, sc, n_tris)) {
-            pol.commit(ray, tag, true, L.best);
+            if (SINGLE) L.best.inst &= kInstMask;
+            pol.commit(ray, tag, true, L.best, kKindUnknown);
             active = false;
             if (STAGE && staged) take_staged();
           }

@@ -482,6 +482,262 @@ float half_to_float(uint16_t h) {
   return f;
 }
 
+
+// ---------------------------------------------------------------------------------------------- JPEG (baseline)
+// The reference reads jpg textures / env maps through stb_image (src/core/texture.cpp:307-336).  This is a baseline
+// sequential decoder (SOF0 / SOF1, 8-bit, Huffman, 1 or 3 components, any sampling factors up to 4x4, restart
+// intervals): float IDCT, stb-style triangle-filter chroma upsampling, JFIF YCbCr -> RGB.  Progressive files (SOF2) are rejected by name.
+struct JpegDecoder {
+  const uint8_t* d;
+  size_t n, p = 0;
+  std::string name;
+  struct Huff {
+    uint8_t bits[17] = {0};
+    uint8_t vals[256] = {0};
+    int mincode[17], maxcode[18], valptr[17];
+    bool set = false;
+    void build() {
+      int code = 0, k = 0;
+      for (int l = 1; l <= 16; l++) {
+        valptr[l] = k, mincode[l] = code;
+        code += bits[l], k += bits[l];
+        maxcode[l] = bits[l] ? code - 1 : -1;
+        code <<= 1;
+      }
+      maxcode[17] = 0x7FFFFFFF;
+      set = true;
+    }
+  } dc[4], ac[4];
+  struct Comp {
+    int id = 0, h = 1, v = 1, tq = 0, td = 0, ta = 0, pred = 0, bw = 0, bh = 0;
+    std::vector<uint8_t> px;  // bw*8 x bh*8 samples
+  } comp[3];
+  uint16_t qt[4][64];
+  bool qt_set[4] = {false, false, false, false};
+  int w = 0, h = 0, nc = 0, hmax = 1, vmax = 1, restart = 0;
+  uint32_t bitbuf = 0;
+  int bitcnt = 0;
+  bool hit_marker = false;
+
+  [[noreturn]] void fail(const std::string& why) const { throw std::runtime_error(name + ": " + why); }
+  uint8_t u8() {
+    if (p >= n) fail("truncated JPEG");
+    return d[p++];
+  }
+  int u16() {
+    int a = u8();
+    return (a << 8) | u8();
+  }
+  int bit() {
+    if (bitcnt == 0) {
+      uint8_t b = 0;
+      if (!hit_marker && p < n) {
+        b = d[p++];
+        if (b == 0xFF) {
+          uint8_t m = p < n ? d[p] : 0;
+          if (m == 0) p++;  // stuffed zero
+          else hit_marker = true, p--, b = 0;  // a marker ends the entropy-coded segment: feed zeros
+        }
+      }
+      bitbuf = b, bitcnt = 8;
+    }
+    bitcnt--;
+    return (bitbuf >> bitcnt) & 1;
+  }
+  int receive(int s) {
+    int v = 0;
+    for (int i = 0; i < s; i++) v = (v << 1) | bit();
+    return v;
+  }
+  static int extend(int v, int s) { return s && v < (1 << (s - 1)) ? v - (1 << s) + 1 : v; }
+  int decode(const Huff& t) {
+    int code = 0;
+    for (int l = 1; l <= 16; l++) {
+      code = (code << 1) | bit();
+      if (t.maxcode[l] >= 0 && code <= t.maxcode[l] && code >= t.mincode[l]) return t.vals[t.valptr[l] + code - t.mincode[l]];
+    }
+    fail("bad Huffman code in JPEG");
+  }
+  static void idct8x8(const float* in, uint8_t* out, int stride) {
+    static float c[8][8];
+    static bool init = false;
+    if (!init) {
+      for (int x = 0; x < 8; x++)
+        for (int u = 0; u < 8; u++) c[x][u] = (u == 0 ? std::sqrt(0.125f) : 0.5f) * std::cos((2 * x + 1) * u * 3.14159265358979f / 16.0f);
+      init = true;
+    }
+    float tmp[64];
+    for (int y = 0; y < 8; y++)  // rows
+      for (int x = 0; x < 8; x++) {
+        float s = 0.f;
+        for (int u = 0; u < 8; u++) s += c[x][u] * in[y * 8 + u];
+        tmp[y * 8 + x] = s;
+      }
+    for (int x = 0; x < 8; x++)  // columns
+      for (int y = 0; y < 8; y++) {
+        float s = 0.f;
+        for (int v = 0; v < 8; v++) s += c[y][v] * tmp[v * 8 + x];
+        int q = (int)std::lround(s + 128.0f);
+        out[y * stride + x] = (uint8_t)std::min(255, std::max(0, q));
+      }
+  }
+  void decode_block(Comp& cp, int bx, int by) {
+    static const uint8_t zz[64] = {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48,
+                                   41, 34, 27, 20, 13, 6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23,
+                                   30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63};
+    float blk[64] = {0};
+    int t = decode(dc[cp.td]);
+    cp.pred += extend(receive(t), t);
+    blk[0] = (float)(cp.pred * qt[cp.tq][0]);
+    for (int k = 1; k < 64;) {
+      int rs = decode(ac[cp.ta]), r = rs >> 4, sz = rs & 15;
+      if (sz == 0) {
+        if (r != 15) break;  // EOB
+        k += 16;
+        continue;
+      }
+      k += r;
+      if (k > 63) fail("bad AC run in JPEG");
+      blk[zz[k]] = (float)(extend(receive(sz), sz) * qt[cp.tq][k]);
+      k++;
+    }
+    idct8x8(blk, &cp.px[((size_t)by * 8) * ((size_t)cp.bw * 8) + (size_t)bx * 8], cp.bw * 8);
+  }
+  void scan() {
+    const int mcux = (w + 8 * hmax - 1) / (8 * hmax), mcuy = (h + 8 * vmax - 1) / (8 * vmax);
+    for (int c = 0; c < nc; c++) {
+      comp[c].bw = mcux * comp[c].h, comp[c].bh = mcuy * comp[c].v;
+      comp[c].px.assign((size_t)comp[c].bw * 8 * comp[c].bh * 8, 0);
+      comp[c].pred = 0;
+      if (!qt_set[comp[c].tq] || !dc[comp[c].td].set || !ac[comp[c].ta].set) fail("JPEG scan refers to a missing table");
+    }
+    bitcnt = 0, hit_marker = false;
+    int count = 0;
+    for (int my = 0; my < mcuy; my++)
+      for (int mx = 0; mx < mcux; mx++) {
+        if (restart && count && count % restart == 0) {  // RSTn: byte-align, skip the marker, reset predictors
+          bitcnt = 0, hit_marker = false;
+          while (p + 1 < n && !(d[p] == 0xFF && d[p + 1] >= 0xD0 && d[p + 1] <= 0xD7)) p++;
+          p += 2;
+          for (int c = 0; c < nc; c++) comp[c].pred = 0;
+        }
+        for (int c = 0; c < nc; c++)
+          for (int v = 0; v < comp[c].v; v++)
+            for (int hh = 0; hh < comp[c].h; hh++) decode_block(comp[c], mx * comp[c].h + hh, my * comp[c].v + v);
+        count++;
+      }
+  }
+  // returns w*h*nc interleaved 8-bit samples (nc = 1 grey, 3 RGB)
+  std::vector<uint8_t> run() {
+    if (n < 4 || d[0] != 0xFF || d[1] != 0xD8) fail("not a JPEG file");
+    p = 2;
+    bool have_frame = false, done = false;
+    while (!done) {
+      while (p < n && d[p] != 0xFF) p++;
+      while (p < n && d[p] == 0xFF) p++;
+      if (p >= n) fail("JPEG without a scan");
+      int m = d[p++];
+      if (m == 0xD9) break;
+      if (m == 0x01 || (m >= 0xD0 && m <= 0xD7)) continue;
+      int len = u16();
+      if (len < 2 || p + (size_t)len - 2 > n) fail("truncated JPEG segment");
+      size_t end = p + (size_t)len - 2;
+      if (m == 0xC0 || m == 0xC1) {
+        if (u8() != 8) fail("only 8-bit JPEG is supported");
+        h = u16(), w = u16(), nc = u8();
+        if (w <= 0 || h <= 0 || (nc != 1 && nc != 3) || (uint64_t)w * h > (1ull << 28)) fail("unsupported JPEG frame");
+        for (int c = 0; c < nc; c++) {
+          comp[c].id = u8();
+          int hv = u8();
+          comp[c].h = hv >> 4, comp[c].v = hv & 15, comp[c].tq = u8() & 3;
+          if (comp[c].h < 1 || comp[c].h > 4 || comp[c].v < 1 || comp[c].v > 4) fail("bad JPEG sampling factors");
+          hmax = std::max(hmax, comp[c].h), vmax = std::max(vmax, comp[c].v);
+        }
+        have_frame = true;
+      } else if (m == 0xC2 || (m >= 0xC3 && m <= 0xCF && m != 0xC4 && m != 0xC8 && m != 0xCC)) {
+        fail("progressive / lossless / arithmetic-coded JPEG is not supported (baseline only) -- re-save it as baseline or png");
+      } else if (m == 0xC4) {
+        while (p < end) {
+          int tc_th = u8(), cls = tc_th >> 4, id = tc_th & 3;
+          Huff& t = cls ? ac[id] : dc[id];
+          int total = 0;
+          for (int l = 1; l <= 16; l++) t.bits[l] = u8(), total += t.bits[l];
+          if (total > 256) fail("bad JPEG Huffman table");
+          for (int i = 0; i < total; i++) t.vals[i] = u8();
+          t.build();
+        }
+      } else if (m == 0xDB) {
+        while (p < end) {
+          int pq_tq = u8(), id = pq_tq & 3;
+          for (int i = 0; i < 64; i++) qt[id][i] = (pq_tq >> 4) ? (uint16_t)u16() : u8();
+          qt_set[id] = true;
+        }
+      } else if (m == 0xDD) {
+        restart = u16();
+      } else if (m == 0xDA) {
+        if (!have_frame) fail("JPEG scan before frame header");
+        int ns = u8();
+        if (ns != nc) fail("multi-scan baseline JPEG is not supported");
+        for (int i = 0; i < ns; i++) {
+          int id = u8(), tt = u8();
+          for (int c = 0; c < nc; c++)
+            if (comp[c].id == id) comp[c].td = tt >> 4, comp[c].ta = tt & 15;
+        }
+        p += 3;  // Ss, Se, Ah/Al
+        scan();
+        done = true;
+        continue;
+      }
+      p = end;
+    }
+    if (!done) fail("JPEG without image data");
+    // chroma upsampling as stb_image does it (the decoder the reference uses): 2x factors through the centred triangle
+    // filter (3 near + 1 far per axis, stbi__resample_row_h_2 / _v_2 / _hv_2), anything else by replication
+    std::vector<std::vector<uint8_t>> full((size_t)nc);
+    for (int c = 0; c < nc; c++) {
+      const Comp& cp = comp[c];
+      const int fx = hmax / cp.h, fy = vmax / cp.v, stride = cp.bw * 8;
+      const int cw = (w * cp.h + hmax - 1) / hmax, ch = (h * cp.v + vmax - 1) / vmax;
+      full[(size_t)c].resize((size_t)w * h);
+      auto at = [&](int x, int y) { return (int)cp.px[(size_t)std::min(std::max(y, 0), ch - 1) * stride + std::min(std::max(x, 0), cw - 1)]; };
+      const bool exact = hmax % cp.h == 0 && vmax % cp.v == 0;
+      for (int y = 0; y < h; y++)
+        for (int x = 0; x < w; x++) {
+          int v;
+          if (exact && fx == 2 && fy == 2) {
+            const int cx = x >> 1, cy = y >> 1, nx = (x & 1) ? cx + 1 : cx - 1, ny = (y & 1) ? cy + 1 : cy - 1;
+            const int t_near = 3 * at(cx, cy) + at(cx, ny), t_far = 3 * at(nx, cy) + at(nx, ny);
+            v = (x == 0 || x == 2 * cw - 1) ? (t_near + 2) >> 2 : (3 * t_near + t_far + 8) >> 4;
+          } else if (exact && fx == 2 && fy == 1) {
+            const int cx = x >> 1, nx = (x & 1) ? cx + 1 : cx - 1;
+            v = (x == 0 || x == 2 * cw - 1) ? at(cx, y) : (3 * at(cx, y) + at(nx, y) + 2) >> 2;
+          } else if (exact && fx == 1 && fy == 2) {
+            const int cy = y >> 1, ny = (y & 1) ? cy + 1 : cy - 1;
+            v = (3 * at(x, cy) + at(x, ny) + 2) >> 2;
+          } else {
+            v = at(x * cp.h / hmax, y * cp.v / vmax);
+          }
+          full[(size_t)c][(size_t)y * w + x] = (uint8_t)v;
+        }
+    }
+    std::vector<uint8_t> out((size_t)w * h * nc);
+    for (int y = 0; y < h; y++)
+      for (int x = 0; x < w; x++) {
+        float s[3] = {0, 0, 0};
+        for (int c = 0; c < nc; c++) s[c] = full[(size_t)c][(size_t)y * w + x];
+        uint8_t* o = &out[((size_t)y * w + x) * nc];
+        if (nc == 1) {
+          o[0] = (uint8_t)s[0];
+        } else {  // JFIF: full-range BT.601
+          float Y = s[0], cb = s[1] - 128.f, cr = s[2] - 128.f;
+          float rgb[3] = {Y + 1.402f * cr, Y - 0.344136f * cb - 0.714136f * cr, Y + 1.772f * cb};
+          for (int k = 0; k < 3; k++) o[k] = (uint8_t)std::min(255.f, std::max(0.f, std::round(rgb[k])));
+        }
+      }
+    return out;
+  }
+};
+
 ImageF read_image(const std::string& path, float gamma) {
   std::string ext = lower_ext(path);
   std::vector<uint8_t> f = read_file(path);
@@ -511,8 +767,22 @@ ImageF read_image(const std::string& path, float gamma) {
     }
     return img;
   }
-  throw std::runtime_error("textures only support extensions (hdr exr png pfm npy) while [" + ext + "] is passed in (" + path +
-                           "; jpg needs a decoder this host does not ship -- convert it to png)");
+  if (ext == "jpg" || ext == "jpeg") {
+    std::vector<uint8_t> f = read_file(path);
+    JpegDecoder j;
+    j.d = f.data(), j.n = f.size(), j.name = path;
+    std::vector<uint8_t> px = j.run();
+    ImageF img;
+    img.w = j.w, img.h = j.h, img.px.resize((size_t)j.w * j.h * 4);
+    const float inv = 1.0f / 255.0f;
+    for (size_t i = 0; i < (size_t)j.w * j.h; i++) {
+      uint8_t r = px[i * j.nc], g = j.nc == 3 ? px[i * 3 + 1] : r, b = j.nc == 3 ? px[i * 3 + 2] : r;
+      float* o = &img.px[4 * i];
+      o[0] = std::pow(r * inv, gamma), o[1] = std::pow(g * inv, gamma), o[2] = std::pow(b * inv, gamma), o[3] = 1.0f;
+    }
+    return img;
+  }
+  throw std::runtime_error("textures only support extensions (hdr exr png jpg pfm npy) while [" + ext + "] is passed in (" + path + ")");
 }
 
 void write_image(const std::string& path, int w, int h, const float* rgba) {

@@ -205,9 +205,13 @@ def test_bvh_is_a_valid_tree(gpu_ctx, which):
     n_inst_tris = sum(len(sc.meshes[m][1]) // 3 for _, m, _, _ in sc.instances)
     assert len(tris) == n_inst_tris and (r["refs"] == 1).all(), (len(tris), n_inst_tris, np.bincount(r["refs"]))
     assert r["outside"] == 0
-    pairs = tris["inst"].astype(np.uint64) << np.uint64(32) | tris["prim"].astype(np.uint64)
+    inst = tris["inst"] & 0x0FFFFFFF  # the top four bits of the word carry the instance's hit kind (miss 0, emitter 1, 2 + material type)
+    kinds = tris["inst"] >> 28
+    want_kind = np.array([1 if light >= 0 else 2 + int(sc.materials[mat]["type"]) for _, _, mat, light in sc.instances])
+    assert np.array_equal(kinds, want_kind[inst])
+    pairs = inst.astype(np.uint64) << np.uint64(32) | tris["prim"].astype(np.uint64)
     assert len(np.unique(pairs)) == len(pairs)
-    per_inst = np.bincount(tris["inst"], minlength=len(sc.instances))
+    per_inst = np.bincount(inst, minlength=len(sc.instances))
     assert [int(c) for c in per_inst] == [len(sc.meshes[m][1]) // 3 for _, m, _, _ in sc.instances]
     st = gpu_ctx.accel_stats()
     assert r["nodes_used"] == st["nodes"] and r["max_depth"] <= 24
