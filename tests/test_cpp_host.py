@@ -211,6 +211,39 @@ def test_hdr_exr_pfm_round_trips(cli, tmp_path):
     assert np.array_equal(np.load(str(tmp_path / "f_pfm.npy"))[..., :3], f[..., :3])
 
 
+def test_jpeg_reader_against_libjpeg(cli, tmp_path):
+    """The reference reads jpg textures through stb_image (src/core/texture.cpp:307-336); the host's baseline JPEG decoder
+    against libjpeg (PIL) on 4:4:4 / 4:2:0 / 4:2:2 / greyscale / optimised-Huffman / restart-interval files: within 3 of
+    255 (IDCT and chroma-filter rounding), and gamma applied like the PNG path.  Progressive files are refused by name."""
+    from PIL import Image
+    import cv2
+    rng = np.random.RandomState(3)
+    y, x = np.mgrid[0:37, 0:53]
+    img = np.stack([(np.sin(x / 7.0) * 0.5 + 0.5) * 255, (np.cos(y / 5.0) * 0.5 + 0.5) * 255, ((x + y) % 64) * 4], -1).astype(np.uint8)
+    img[10:20, 10:30] = rng.randint(0, 255, (10, 20, 3))
+    cases = {"444": dict(quality=95, subsampling=0), "420": dict(quality=90, subsampling=2), "422": dict(quality=85, subsampling=1),
+             "opt": dict(quality=92, subsampling=0, optimize=True), "grey": dict(quality=90)}
+    for name, kw in cases.items():
+        path = str(tmp_path / f"{name}.jpg")
+        Image.fromarray(img[..., 0] if name == "grey" else img).save(path, **kw)
+        _convert(cli, path, str(tmp_path / f"{name}.npy"))
+        got = np.load(str(tmp_path / f"{name}.npy"))
+        ref = np.asarray(Image.open(path).convert("RGB"), np.float32) / 255
+        assert got.shape == (37, 53, 4) and np.all(got[..., 3] == 1)
+        assert np.abs(got[..., :3] - ref).max() <= 3.01 / 255, name
+    path = str(tmp_path / "rst.jpg")
+    if cv2.imwrite(path, img[..., ::-1], [cv2.IMWRITE_JPEG_QUALITY, 90, cv2.IMWRITE_JPEG_RST_INTERVAL, 4]):
+        _convert(cli, path, str(tmp_path / "rst.npy"))
+        ref = np.asarray(Image.open(path).convert("RGB"), np.float32) / 255
+        assert np.abs(np.load(str(tmp_path / "rst.npy"))[..., :3] - ref).max() <= 3.01 / 255
+    _convert(cli, str(tmp_path / "444.jpg"), str(tmp_path / "g.npy"), 2.2)
+    ref = (np.asarray(Image.open(str(tmp_path / "444.jpg")).convert("RGB"), np.float32) / 255) ** 2.2
+    assert np.abs(np.load(str(tmp_path / "g.npy"))[..., :3] - ref).max() <= 0.03
+    Image.fromarray(img).save(str(tmp_path / "prog.jpg"), progressive=True)
+    r = subprocess.run([cli, "--scene", "-", "--convert", str(tmp_path / "prog.jpg"), str(tmp_path / "p.npy")], capture_output=True, text=True)
+    assert r.returncode != 0 and "progressive" in r.stderr
+
+
 def test_tone_mappers_match_closed_forms(cli, tmp_path):
     """reference src/shaders/post.idle.frag:76-133"""
     x = np.ones((1, 64, 4), np.float32)
