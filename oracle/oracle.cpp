@@ -14,10 +14,12 @@
 // bench.py's cpu_baseline / --impl reference legs may load this library; the product
 // (asuna_b200/) never does.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, tests or scenes for this path and
-// cannot be built or run in this environment (no Vulkan loader/ICD, no glslang).
-// The only external anchors are the published PCG / xxHash32 constants; everything else is
-// pinned by this restatement itself (tests/golden/ holds vectors frozen from it).
+// PARITY PINNED TO THE REFERENCE'S OWN SHADERS: the reference ships no golden vectors, tests or scenes for this path
+// and cannot be built or run as a whole in this environment (no Vulkan loader/ICD, no glslang), but its
+// GLSL can be compiled as C++ against the GLM it vendors (oracle/refbuild/build_ref.py -> oracle/_ref/libref.so = this
+// file built with -DASUNA_REF_SHADERS + the generated shader unit).  tests/test_ref_pins.py holds every function and every
+// shader main() below to that library (integer work bit-exact, fp32 within stated bounds), and tests/golden/ref_* holds
+// vectors frozen FROM it.  Further anchors: published PCG / xxHash32 constants, closed forms of the rendering equation.
 //
 // Deliberate deviations from the shader text, all behaviour-neutral
 // on the measured configs:
