@@ -1105,6 +1105,129 @@ int asuna_debug_download_accel(asuna_ctx* ctx, void* nodes_out, void* tris_out) 
   if (tris_out) ASUNA_CUDA_CHECK(cudaMemcpy(tris_out, ctx->d_tris, ctx->pool_tris * sizeof(TriSlot), cudaMemcpyDeviceToHost));
   return 0;
 }
+
+// Test hook: ONE shade-kernel invocation per caller-made path (tests/test_gpu_ref_parity.py).  Mirrors oracle_shade_probes /
+// refglsl_shade_probe (oracle/refbuild/ref_bridge.h, same ShadeProbe layout): the payload as it enters a closest-hit or
+// miss shader goes into path slot i, the hit record is given (inst = 0xFFFFFFFF: miss), the regroup + per-kind shade
+// kernels of one bounce run, and the payload is read back from the path state, the next queue (stop), the shadow queue
+// (direct-light record) and the AOV planes.  What the wavefront form does not keep is returned as it came in: the RNG
+// state / next ray / throughput of a path that stopped, the radiance of a zero NEE contribution (skip = 1, A.3-4).
+struct AsunaShadeProbe {
+  float ray_o[3], ray_d[3], radiance[3], throughput[3];
+  uint32_t depth, seed, stop;
+  float brec_d[3], brec_pdf;
+  uint32_t brec_flags;
+  float drec_radiance[3], drec_dist, drec_o[3], drec_d[3];
+  uint32_t drec_skip;
+  float channel[8][3];
+};
+int asuna_debug_shade_probes(asuna_ctx* ctx, uint32_t n, const uint32_t* inst, const uint32_t* prim, const float* b1,
+                             const float* b2, AsunaShadeProbe* q) {
+  if (ctx->scene_dirty) return fail(ctx, ASUNA_E_INVALID, "scene not built");
+  if (n == 0) return 0;
+  if (ctx->W == 0 || n > ctx->W * ctx->H) return fail(ctx, ASUNA_E_INVALID, "shade probes need a film of at least n pixels");
+  cudaSetDevice(ctx->device);
+  cudaStream_t s = ctx->stream;
+  int rc = ensure_path_buffers(ctx, ctx->W * ctx->H);
+  if (rc) return rc;
+  std::vector<float4> ro(n), rd(n), th(n), ra(n);
+  std::vector<uint4> hit(n);
+  std::vector<uint32_t> queue(n);
+  std::vector<uint8_t> kind(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const AsunaShadeProbe& p = q[i];
+    uint32_t seed = p.seed, packed = (p.depth & 0xFFFFu) | (p.brec_flags << 16);
+    float fs, fp_;
+    memcpy(&fs, &seed, 4), memcpy(&fp_, &packed, 4);
+    ro[i] = make_float4(p.ray_o[0], p.ray_o[1], p.ray_o[2], fs);
+    rd[i] = make_float4(p.ray_d[0], p.ray_d[1], p.ray_d[2], p.brec_pdf);
+    th[i] = make_float4(p.throughput[0], p.throughput[1], p.throughput[2], fp_);
+    ra[i] = make_float4(p.radiance[0], p.radiance[1], p.radiance[2], 0.f);
+    uint32_t ub1, ub2;
+    memcpy(&ub1, &b1[i], 4), memcpy(&ub2, &b2[i], 4);
+    hit[i] = make_uint4(ub1, ub2, inst[i], prim[i]);
+    queue[i] = i;
+    if (inst[i] == 0xFFFFFFFFu) {
+      kind[i] = (uint8_t)kKindMiss;
+    } else {
+      if (inst[i] >= ctx->instances.size()) return fail(ctx, ASUNA_E_INVALID, "probe refers to unknown instance");
+      const HostInstance& in = ctx->instances[inst[i]];
+      if (prim[i] >= ctx->meshes[in.mesh].n_tris) return fail(ctx, ASUNA_E_INVALID, "probe refers to unknown primitive");
+      kind[i] = (uint8_t)(in.light >= 0 ? (uint32_t)kKindLight : kKindMaterial0 + ctx->materials[in.material].type);
+    }
+  }
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->ps.ray_o, ro.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->ps.ray_d, rd.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->ps.thr, th.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->ps.rad, ra.data(), n * sizeof(float4), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->ps.hit, hit.data(), n * sizeof(uint4), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->ps.queue[0], queue.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->ps.kind, kind.data(), n, cudaMemcpyHostToDevice, s));
+  ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->d_counters, 0, sizeof(Counters), s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(&ctx->d_counters->queue[0], &n, sizeof(uint32_t), cudaMemcpyHostToDevice, s));
+  const size_t plane = (size_t)ctx->W * ctx->H * sizeof(float4);
+  for (int c = 1; c < ASUNA_NUM_OUTPUT_IMAGES - 1; c++) ASUNA_CUDA_CHECK(cudaMemsetAsync(ctx->out.img[c], 0, plane, s));
+  FrameParams fp = make_frame_params(ctx);
+  fp.n_frames = 1;
+  fp.frame_ids[0] = 0;  // frame 0: AOVs are stored for depth-1 probes, at pixel = probe index
+  fp.first_is_replace = 1;
+  fp.pc.curFrame = 0;
+  fp.pc.maxPathDepth = 1000;  // "stop" below is then the shader's own decision, never the depth limit
+  uint32_t mask = 1u << kKindMiss;
+  for (uint32_t i = 0; i < n; i++) mask |= 1u << kind[i];
+  launch_shade(s, ctx->dims, ctx->view, fp, ctx->ps, ctx->out, ctx->d_counters, 0, 0, mask, n);
+  uint32_t n_next = 0, n_shadow = 0;
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(&n_next, &ctx->d_counters->queue[1], sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(&n_shadow, &ctx->d_counters->shadow[0], sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ro.data(), ctx->ps.ray_o, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(rd.data(), ctx->ps.ray_d, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(th.data(), ctx->ps.thr, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ra.data(), ctx->ps.rad, n * sizeof(float4), cudaMemcpyDeviceToHost, s));
+  ASUNA_CUDA_CHECK(cudaStreamSynchronize(s));
+  ASUNA_CUDA_CHECK(cudaGetLastError());
+  if (n_next > n || n_shadow > n) return fail(ctx, ASUNA_E_CUDA, "shade probe: queue counters out of range");
+  std::vector<uint32_t> next(n_next);
+  std::vector<float4> so(n_shadow), sd(n_shadow), sl(n_shadow);
+  if (n_next) ASUNA_CUDA_CHECK(cudaMemcpy(next.data(), ctx->ps.queue[1], n_next * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  if (n_shadow) {
+    ASUNA_CUDA_CHECK(cudaMemcpy(so.data(), ctx->ps.sh_o, n_shadow * sizeof(float4), cudaMemcpyDeviceToHost));
+    ASUNA_CUDA_CHECK(cudaMemcpy(sd.data(), ctx->ps.sh_d, n_shadow * sizeof(float4), cudaMemcpyDeviceToHost));
+    ASUNA_CUDA_CHECK(cudaMemcpy(sl.data(), ctx->ps.sh_l, n_shadow * sizeof(float4), cudaMemcpyDeviceToHost));
+  }
+  std::vector<float4> aov((size_t)n);
+  for (uint32_t i = 0; i < n; i++) q[i].stop = 1, q[i].drec_skip = 1;
+  for (uint32_t k : next) {
+    if (k >= n) return fail(ctx, ASUNA_E_CUDA, "shade probe: bad slot in the next queue");
+    AsunaShadeProbe& p = q[k];
+    p.stop = 0;
+    uint32_t packed, seed;
+    memcpy(&packed, &th[k].w, 4), memcpy(&seed, &ro[k].w, 4);
+    p.ray_o[0] = ro[k].x, p.ray_o[1] = ro[k].y, p.ray_o[2] = ro[k].z, p.seed = seed;
+    p.ray_d[0] = p.brec_d[0] = rd[k].x, p.ray_d[1] = p.brec_d[1] = rd[k].y, p.ray_d[2] = p.brec_d[2] = rd[k].z;
+    p.brec_pdf = rd[k].w;
+    p.throughput[0] = th[k].x, p.throughput[1] = th[k].y, p.throughput[2] = th[k].z;
+    p.depth = (packed & 0xFFFFu) - 1u;  // the kernel stores rgen's depth++ already
+    p.brec_flags = packed >> 16;
+  }
+  for (uint32_t i = 0; i < n; i++) q[i].radiance[0] = ra[i].x, q[i].radiance[1] = ra[i].y, q[i].radiance[2] = ra[i].z;
+  for (uint32_t j = 0; j < n_shadow; j++) {
+    uint32_t k;
+    memcpy(&k, &sd[j].w, 4);
+    if (k >= n) return fail(ctx, ASUNA_E_CUDA, "shade probe: bad slot in the shadow queue");
+    AsunaShadeProbe& p = q[k];
+    p.drec_skip = 0;
+    p.drec_radiance[0] = sl[j].x, p.drec_radiance[1] = sl[j].y, p.drec_radiance[2] = sl[j].z;
+    p.drec_o[0] = so[j].x, p.drec_o[1] = so[j].y, p.drec_o[2] = so[j].z;
+    p.drec_d[0] = sd[j].x, p.drec_d[1] = sd[j].y, p.drec_d[2] = sd[j].z;
+    p.drec_dist = so[j].w + 2.0f * 0.001f;  // the queue holds tmax = dist - 2 EPS (rgen:119)
+  }
+  for (uint32_t c = 0; c < 7; c++) {
+    ASUNA_CUDA_CHECK(cudaMemcpy(aov.data(), ctx->out.img[c + 1], (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost));
+    for (uint32_t i = 0; i < n; i++) q[i].channel[c][0] = aov[i].x, q[i].channel[c][1] = aov[i].y, q[i].channel[c][2] = aov[i].z;
+  }
+  ctx->have_accum = false;
+  return 0;
+}
 int asuna_debug_radix_sort(asuna_ctx* ctx, uint64_t* keys, uint32_t* vals, uint32_t n) {
   if (n == 0) return 0;
   cudaSetDevice(ctx->device);
