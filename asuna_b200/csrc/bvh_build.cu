@@ -649,20 +649,34 @@ __device__ void emit_wide_node(const EmitParams& a, uint32_t w, bool valid) {
       dz[i] = 0.5f * (clo[i].z + chi[i].z) - cz;
       slot_of[i] = -1;
     }
-    uint32_t slot_used = 0;
-    for (int round = 0; round < nc; round++) {
-      float best = -FLT_MAX;
-      int bi = 0, bs = 0;
-      for (int i = 0; i < nc; i++) {
-        if (slot_of[i] >= 0) continue;
-        for (int s = 0; s < 8; s++) {
-          if (slot_used & (1u << s)) continue;
-          float v = ((s & 1) ? dx[i] : -dx[i]) + ((s & 2) ? dy[i] : -dy[i]) + ((s & 4) ? dz[i] : -dz[i]);
-          if (v > best) best = v, bi = i, bs = s;
-        }
+    // all loops have constant bounds and are fully unrolled, so the 8 x 8 score table and the bookkeeping live in
+    // registers: the dynamically indexed form kept everything in local memory, and this assignment is the longest
+    // serial stretch of a thread that a whole level's barrier waits for
+    float score[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+      for (int sl = 0; sl < 8; sl++)
+        score[i][sl] = i < nc ? ((sl & 1) ? dx[i] : -dx[i]) + ((sl & 2) ? dy[i] : -dy[i]) + ((sl & 4) ? dz[i] : -dz[i]) : -FLT_MAX;
+    uint32_t slot_used = 0, child_done = 0;
+#pragma unroll
+    for (int round = 0; round < 8; round++) {
+      if (round < nc) {
+        float best = -FLT_MAX;
+        int bi = 0, bs = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+          for (int sl = 0; sl < 8; sl++) {
+            const bool free_pair = i < nc && !((child_done >> i) & 1u) && !((slot_used >> sl) & 1u);
+            if (free_pair && score[i][sl] > best) best = score[i][sl], bi = i, bs = sl;
+          }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+          if (i == bi) slot_of[i] = bs;
+        slot_used |= 1u << bs;
+        child_done |= 1u << bi;
       }
-      slot_of[bi] = bs;
-      slot_used |= 1u << bs;
     }
   }
   int child_in_slot[8];
@@ -770,7 +784,11 @@ __device__ void emit_wide_node(const EmitParams& a, uint32_t w, bool valid) {
   out[4] = make_uint4(pack4(nd.qhiy), pack4(nd.qhiy + 4), pack4(nd.qhiz), pack4(nd.qhiz + 4));
 }
 
-__global__ void __launch_bounds__(kThreads) k_emit_wide(const EmitParams a) {
+// Two builds of the same kernel: MIN_BLOCKS = 2 keeps the unrolled slot assignment in registers (104 of them) and is
+// 6-9 % faster up to a few million primitives, where a level's barrier waits for the slowest thread; MIN_BLOCKS = 4
+// (64 registers, twice the resident warps) wins on the 32.8 M-triangle build, which is throughput-bound (25.4 vs 26.2 ms).
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(kThreads, MIN_BLOCKS) k_emit_wide(const EmitParams a) {
   cg::grid_group grid = cg::this_grid();
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, gsize = gridDim.x * blockDim.x;
   if (gtid == 0) {
@@ -832,13 +850,16 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     if ((e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_a, k_ploc, kThreads, 0)) != cudaSuccess) return e;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_emit_wide, kThreads, 0)) != cudaSuccess) return e;
+    int per_sm_c = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_emit_wide<4>, kThreads, 0)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_emit_wide<2>, kThreads, 0)) != cudaSuccess) return e;
     // each cooperative kernel gets the largest co-resident grid IT fits: both walk trees through dependent, scattered
     // loads, so resident warps are what hides their latency (ASUNA_BUILD_BLOCKS_PER_SM caps both, for experiments)
     int cap_blocks = 4;  // measured on B200: 3 / 4 / 6 / 8 blocks per SM -> 26.9 / 25.5 / 25.9 / 25.8 ms at 32.8 M triangles, 2.15 / 2.11 / 2.18 / 2.18 ms at 1.31 M
     if (const char* t = getenv("ASUNA_BUILD_BLOCKS_PER_SM")) cap_blocks = std::max(1, atoi(t));
     coop_blocks = (uint32_t)(sms * std::max(1, std::min(per_sm_a, cap_blocks)));
     coop_blocks_emit = (uint32_t)(sms * std::max(1, std::min(per_sm_b, cap_blocks)));
+    coop_blocks_emit_small = (uint32_t)(sms * std::max(1, std::min(per_sm_c, cap_blocks)));
   }
   if (n <= capacity) return cudaSuccess;
   release();
@@ -952,8 +973,10 @@ cudaError_t launch_build_wide(cudaStream_t s, uint32_t n, WideNode* nodes, uint3
   ep.soup = payload.soup, ep.prim_ids = payload.prim_ids;
   ep.out_lo = root_lo, ep.out_hi = root_hi, ep.result = result;
   void* eargs[] = {&ep};
-  const uint32_t grid_emit = std::max(1u, std::min(sc.coop_blocks_emit, div_up(n, kThreads)));
-  return cudaLaunchCooperativeKernel((const void*)k_emit_wide, dim3(grid_emit), dim3(kThreads), eargs, 0, s);
+  const bool small = n <= (4u << 20);
+  const uint32_t grid_emit = std::max(1u, std::min(small ? sc.coop_blocks_emit_small : sc.coop_blocks_emit, div_up(n, kThreads)));
+  return cudaLaunchCooperativeKernel(small ? (const void*)k_emit_wide<2> : (const void*)k_emit_wide<4>, dim3(grid_emit),
+                                     dim3(kThreads), eargs, 0, s);
 }
 
 // Host-side debug/test hook: sorts (key,value) pairs with the builder's radix sort.

@@ -26,7 +26,8 @@ struct BuildScratch {
   void* arena = nullptr;                   // all of the above live in ONE device allocation (a build pays one cudaMalloc)
   uint32_t capacity = 0;
   uint32_t coop_blocks = 0;                // co-resident grid size of k_ploc ...
-  uint32_t coop_blocks_emit = 0;           // ... and of k_emit_wide
+  uint32_t coop_blocks_emit = 0;           // ... and of k_emit_wide<4> / <2>
+  uint32_t coop_blocks_emit_small = 0;
   ~BuildScratch();
   cudaError_t reserve(uint32_t n);
   void release();
