@@ -194,7 +194,10 @@ def main():
     cmd3 = ["g++", "-shared", "-pthread", "-o", os.path.join(OUT, "libref.so"), os.path.join(OUT, "ref_glsl_gen.o"),
             os.path.join(OUT, "oracle_ref.o"), os.path.join(OUT, "ref_host_gen.o")]
     for cmd in (cmd1, cmd2, cmdh, cmd3):
-        subprocess.check_call(cmd)
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:  # the compilers' warnings about the reference's text are noise unless the build fails
+            sys.stderr.write(r.stdout + r.stderr)
+            raise SystemExit(f"build_ref: {' '.join(cmd[:3])} ... failed with {r.returncode}")
     print("built", os.path.join(OUT, "libref.so"))
     return 0
 
