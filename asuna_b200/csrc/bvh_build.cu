@@ -926,10 +926,15 @@ void launch_instance_boxes(cudaStream_t s, const DInstance* inst, const uint32_t
   k_instance_boxes<<<div_up(n, kThreads), kThreads, 0, s>>>(inst, ids, mesh_lo, mesh_hi, n, sc.blo, sc.bhi, sc.bounds);
 }
 
-static void sort_passes(cudaStream_t s, uint32_t n, BuildScratch& sc) {
+// LSD radix sort of the 64-bit keys from bit `first_shift` up (a multiple of 16, so the pass count stays even and the
+// result lands in buffer 0).  The builder sorts Morton keys of fewer than 16 M primitives on their top 47 bits only
+// (15.7 bits per axis: a 1 / 52 000 grid, two orders of magnitude finer than the primitive spacing such a scene can have;
+// primitives sharing a cell keep their input order and PLOC's neighbour search is insensitive to it -- the SAH-quality
+// test guards this): 6 passes instead of 8.
+static void sort_passes(cudaStream_t s, uint32_t n, BuildScratch& sc, int first_shift = 0) {
   uint32_t sort_blocks = div_up(n, kSortTile);
   int cur = 0;
-  for (int shift = 0; shift < 64; shift += 8) {
+  for (int shift = first_shift; shift < 64; shift += 8) {
     k_sort_hist<<<sort_blocks, kThreads, 0, s>>>(sc.keys[cur], n, shift, sc.hist, sort_blocks);
     uint32_t* totals = sc.hist + 256u * (size_t)sort_blocks;
     k_sort_scan_rows<<<256, kThreads, 0, s>>>(sc.hist, sort_blocks, totals);
@@ -937,7 +942,7 @@ static void sort_passes(cudaStream_t s, uint32_t n, BuildScratch& sc) {
                                                     n, shift, sc.hist, sort_blocks, totals);
     cur ^= 1;
   }
-  // 8 passes: the result is back in buffer 0
+  // an even number of passes: the result is back in buffer 0
 }
 
 // Builds the wide BVH over the n boxes already in sc.blo/bhi (bounds in sc.bounds): nodes[node_base ..) receive the
@@ -947,7 +952,7 @@ cudaError_t launch_build_wide(cudaStream_t s, uint32_t n, WideNode* nodes, uint3
                               float4* root_hi, BuildResult* result) {
   if (n >= 2) {
     k_morton<<<div_up(n, kThreads), kThreads, 0, s>>>(sc.blo, sc.bhi, n, sc.bounds, sc.keys[0], sc.vals[0]);
-    sort_passes(s, n, sc);
+    sort_passes(s, n, sc, n < (1u << 24) ? 16 : 0);
   } else {
     cudaMemsetAsync(sc.vals[0], 0, sizeof(uint32_t), s);
   }
