@@ -99,6 +99,14 @@ k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cn
   ClosestPolicy pol{ps, ps.queue[qsel], sc.instances};
   constexpr bool kStage = SINGLE && ASUNA_TRACE_STAGE;
   __shared__ __align__(16) uint32_t stage[kStage ? (kTraceThreads / 32) * kStageWords * 32 : 4];
+#if ASUNA_TRI_POOL
+  if constexpr (SINGLE) {
+    __shared__ __align__(16) uint32_t pool[(kTraceThreads / 32) * kPoolWordsPerWarp];
+    trace_persistent_pool<COUNT>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow, &cnt->node_visits,
+                                 &cnt->tri_tests, stage, pool);
+    return;
+  }
+#endif
   trace_persistent<false, COUNT, SINGLE, kStage>(sc, pol, cnt->queue[iter], &cnt->ticket_closest[iter], &cnt->stack_overflow,
                                                  &cnt->node_visits, &cnt->tri_tests, cnt->lane_stats, stage);
 }

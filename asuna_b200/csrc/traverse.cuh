@@ -568,4 +568,244 @@ __device__ void trace_persistent(const SceneView& sc, Policy& pol, uint32_t coun
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// EXPERIMENT (ASUNA_TRI_POOL, single-level closest-hit kernel only): triangle tests decoupled from the lane that found
+// them.  A node step's leaf hits are appended to a per-warp pool of (owner lane, triangle slot) items in shared memory;
+// once 32 are pooled (or nobody has node work left) the whole warp tests one triangle per lane with the OWNER's ray
+// constants fetched by indexed shuffles, and the per-ray minima are merged with shared-memory atomics under the same
+// tie-break as the per-lane form (lowest t, then instance, then primitive).  Lanes never hold triangle groups, so the
+// postponing / swapping logic disappears.  Measured against the per-lane form in profiles/README.md.
+#ifndef ASUNA_TRI_POOL
+#define ASUNA_TRI_POOL 0
+#endif
+constexpr int kPoolCap = 128;  // items per warp, power of two (ring buffer)
+#ifndef ASUNA_POOL_FLUSH_MIN
+#define ASUNA_POOL_FLUSH_MIN 16  // a batch also runs with this many items when some lane waits for its triangles
+#endif
+struct PoolMem {  // per warp
+  uint32_t item[kPoolCap];
+  unsigned long long best_key[32];
+  uint32_t best_t[32];
+  float best_b1[32], best_b2[32];
+  uint32_t done[32];
+};
+constexpr int kPoolWordsPerWarp = sizeof(PoolMem) / 4;
+
+template <bool COUNT, class Policy>
+__device__ void trace_persistent_pool(const SceneView& sc, Policy& pol, uint32_t count, uint32_t* ticket, uint32_t* overflow,
+                                      unsigned long long* node_visits, unsigned long long* tri_tests,
+                                      uint32_t* stage_words, uint32_t* pool_words) {
+  const uint32_t lane = threadIdx.x & 31u, lt = (1u << lane) - 1u, warp = threadIdx.x >> 5;
+  uint4* const stg = reinterpret_cast<uint4*>(stage_words) + (warp * 32 + lane) * (kStageWords / 4);
+  PoolMem& P = *reinterpret_cast<PoolMem*>(pool_words + warp * kPoolWordsPerWarp);
+  bool staged = false;
+  Lane L;
+  uint2 stack_local[kStackSize + 1];
+  StackMem stack;
+  stack.local = stack_local;
+#if ASUNA_SMEM_STACK > 0
+  __shared__ uint2 stack_shared_p[ASUNA_SMEM_STACK * kTraceThreads];
+  stack.shared = stack_shared_p + threadIdx.x;
+#endif
+  L.sp = 0, L.blas_sp = 0, L.in_blas = true, L.shear_ok = true;
+  L.ng = L.tg = L.top = make_uint2(0u, 0u);
+  bool active = false, exhausted = (count == 0);
+  uint32_t ray = 0, tag = 0, n_nodes = 0, n_tris = 0, pending = 0;
+  uint32_t p_head = 0, p_count = 0;  // warp-uniform ring state
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t chunk = min((uint32_t)ASUNA_TICKET_CHUNK, max(count / (n_warps * 4u), 1u));
+  uint32_t w_next = 0, w_end = 0;
+  auto take_staged = [&]() {
+    const uint4 a = stg[0], b = stg[1], c = stg[2], d = stg[3], e = stg[4];
+    L.rs.o = f3(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z));
+    L.rs.idir = f3(__uint_as_float(a.w), __uint_as_float(b.x), __uint_as_float(b.y));
+    L.rs.sx = f3(__uint_as_float(b.z), __uint_as_float(b.w), __uint_as_float(c.x));
+    L.rs.sy = f3(__uint_as_float(c.y), __uint_as_float(c.z), __uint_as_float(c.w));
+    L.rs.sz = f3(__uint_as_float(d.x), __uint_as_float(d.y), __uint_as_float(d.z));
+    L.rs.oct = (a.w >> 31) | ((b.x >> 31) << 1) | ((b.y >> 31) << 2);
+    L.tmin = __uint_as_float(d.w), L.tmax = __uint_as_float(e.x);
+    ray = e.y, tag = e.z;
+    L.sp = 0;
+    L.ng = make_uint2(sc.single_root, 0x80000000u);
+    L.tg = make_uint2(0u, 0u);
+    L.best.inst = 0xFFFFFFFFu, L.best.prim = 0xFFFFFFFFu, L.best.b1 = L.best.b2 = L.best.t = 0.f;
+    pending = 0;
+    staged = false;
+    active = true;
+  };
+  for (;;) {
+    // ---- refill the empty prepared-ray slots from the queue
+    const uint32_t idle = __ballot_sync(0xFFFFFFFFu, !staged);
+    if (!exhausted && idle) {
+      const uint32_t n_idle = __popc(idle), avail = w_end - w_next;
+      uint32_t i = w_next + __popc(idle & lt);
+      if (avail < n_idle) {
+        const uint32_t take = max(chunk, n_idle);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(ticket, take);
+        base = __shfl_sync(0xFFFFFFFFu, base, 0);
+        if (i >= w_end) i = base + (i - w_end);
+        w_next = base + (n_idle - avail), w_end = base + take;
+      } else {
+        w_next += n_idle;
+      }
+      if (!staged && i < count) {
+        float3 o, d;
+        float t0, t1;
+        const uint32_t g = pol.load(i, o, d, t0, t1);
+        RaySpace rs;
+        setup_space(rs, o, d);
+        setup_shear(rs, d);
+        stg[0] = make_uint4(__float_as_uint(o.x), __float_as_uint(o.y), __float_as_uint(o.z), __float_as_uint(rs.idir.x));
+        stg[1] = make_uint4(__float_as_uint(rs.idir.y), __float_as_uint(rs.idir.z), __float_as_uint(rs.sx.x), __float_as_uint(rs.sx.y));
+        stg[2] = make_uint4(__float_as_uint(rs.sx.z), __float_as_uint(rs.sy.x), __float_as_uint(rs.sy.y), __float_as_uint(rs.sy.z));
+        stg[3] = make_uint4(__float_as_uint(rs.sz.x), __float_as_uint(rs.sz.y), __float_as_uint(rs.sz.z), __float_as_uint(t0));
+        stg[4] = make_uint4(__float_as_uint(t1), i, g, 0u);
+        staged = true;
+      }
+      if (w_next >= count) exhausted = true;
+    }
+    if (!active && staged) take_staged();
+    if (__ballot_sync(0xFFFFFFFFu, active) == 0u) {
+      if (exhausted && __ballot_sync(0xFFFFFFFFu, staged) == 0u) break;
+      continue;
+    }
+    for (;;) {
+      // ---- pop / finish: a ray is done when it has no node group, an empty stack, nothing held back and no pooled triangle
+      if (active && L.ng.y <= 0x00FFFFFFu && L.tg.y == 0u) {
+        if (L.sp > 0) {
+          L.ng = lane_pop(L, stack);
+        } else if (pending == 0u) {
+          const bool found = L.best.inst != 0xFFFFFFFFu;
+          uint32_t kind = kKindUnknown;
+          if (found) kind = L.best.inst >> 28, L.best.inst &= kInstMask;
+          pol.commit(ray, tag, found, L.best, kind);
+          active = false;
+          if (staged) take_staged();
+        }
+      }
+      const uint32_t m_act = __ballot_sync(0xFFFFFFFFu, active);
+      if (m_act == 0u) break;
+      // ---- one wide-node step for every lane that has a node group (and is not holding triangles back)
+      uint32_t leaf_base = L.tg.x, leaf_mask = L.tg.y;  // held back from an iteration in which the pool was full
+      const bool stepping = active && L.ng.y > 0x00FFFFFFu && L.tg.y == 0u;
+      if (stepping) {
+        const uint32_t hits = L.ng.y;
+        const uint32_t bit = 31u - (uint32_t)__clz(hits);
+        const uint2 rest = make_uint2(L.ng.x, hits & ~(1u << bit));
+        const uint32_t slot = (bit - 24u) ^ 7u ^ L.rs.oct;
+        const uint32_t rel = __popc(hits & 0xFFu & ~(0xFFFFFFFFu << slot));
+        const uint4* np = reinterpret_cast<const uint4*>(sc.blas_nodes + L.ng.x + rel);
+        const uint4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
+        if (COUNT) n_nodes++;
+        if (rest.y > 0x00FFFFFFu) lane_push(L, stack, rest, overflow);
+        const uint32_t mask = intersect_wide_node(n0, n1, n2, n3, n4, L.rs, L.tmin, L.tmax, sc.magic);
+        L.ng = make_uint2(n1.x, (mask & 0xFF000000u) | (n0.w >> 24));
+        leaf_base = n1.y, leaf_mask = mask & 0x00FFFFFFu;
+      }
+      // ---- append the leaf hits to the warp's pool (whole lanes, in lane order, while there is room)
+      if (__ballot_sync(0xFFFFFFFFu, leaf_mask != 0u)) {
+        const uint32_t c = __popc(leaf_mask);
+        uint32_t x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
+          if (lane >= (uint32_t)o) x += y;
+        }
+        const uint32_t total = __shfl_sync(0xFFFFFFFFu, x, 31);
+        if (total) {
+          const uint32_t room = (uint32_t)kPoolCap - p_count;
+          const bool fits = x <= room;  // monotone in the lane index: the lanes that fit form a prefix
+          if (fits) {
+            uint32_t pos = p_head + p_count + (x - c), m = leaf_mask;
+            while (m) {
+              const uint32_t b = (uint32_t)__ffs((int)m) - 1u;
+              m &= m - 1u;
+              P.item[pos++ & (kPoolCap - 1)] = (lane << 27) | (leaf_base + b);
+            }
+            pending += c;
+            L.tg = make_uint2(0u, 0u);
+          } else {
+            L.tg = make_uint2(leaf_base, leaf_mask);
+          }
+          const uint32_t fit_mask = __ballot_sync(0xFFFFFFFFu, fits);
+          const uint32_t added = fit_mask ? __shfl_sync(0xFFFFFFFFu, x, 31 - __clz(fit_mask)) : 0u;
+          p_count += added;
+          __syncwarp();
+        }
+      }
+      // ---- pooled triangle step
+      {
+        const uint32_t m_node = __ballot_sync(0xFFFFFFFFu, active && L.ng.y > 0x00FFFFFFu && L.tg.y == 0u);
+        const uint32_t m_wait = __ballot_sync(0xFFFFFFFFu, active && (L.tg.y != 0u || (L.ng.y <= 0x00FFFFFFu && L.sp == 0 && pending != 0u)));
+        while (p_count >= 32u || (p_count > 0u && (m_node == 0u || (m_wait != 0u && p_count >= (uint32_t)ASUNA_POOL_FLUSH_MIN)))) {
+          const uint32_t nb = min(p_count, 32u);
+          const bool have = lane < nb;
+          const uint32_t it = have ? P.item[(p_head + lane) & (kPoolCap - 1)] : 0u;
+          const uint32_t src = have ? it >> 27 : lane;
+          const TriSlot* tp = sc.tris + (it & 0x07FFFFFFu);
+          float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0, v2 = v0;
+          if (have) v0 = __ldg(&tp->v0), v1 = __ldg(&tp->v1), v2 = __ldg(&tp->v2);
+          RaySpace rs;
+          rs.o = f3(__shfl_sync(0xFFFFFFFFu, L.rs.o.x, src), __shfl_sync(0xFFFFFFFFu, L.rs.o.y, src), __shfl_sync(0xFFFFFFFFu, L.rs.o.z, src));
+          rs.sx = f3(__shfl_sync(0xFFFFFFFFu, L.rs.sx.x, src), __shfl_sync(0xFFFFFFFFu, L.rs.sx.y, src), __shfl_sync(0xFFFFFFFFu, L.rs.sx.z, src));
+          rs.sy = f3(__shfl_sync(0xFFFFFFFFu, L.rs.sy.x, src), __shfl_sync(0xFFFFFFFFu, L.rs.sy.y, src), __shfl_sync(0xFFFFFFFFu, L.rs.sy.z, src));
+          rs.sz = f3(__shfl_sync(0xFFFFFFFFu, L.rs.sz.x, src), __shfl_sync(0xFFFFFFFFu, L.rs.sz.y, src), __shfl_sync(0xFFFFFFFFu, L.rs.sz.z, src));
+          const float src_tmin = __shfl_sync(0xFFFFFFFFu, L.tmin, src), src_tmax = __shfl_sync(0xFFFFFFFFu, L.tmax, src);
+          // owners publish their current best; candidates compete in shared memory
+          const unsigned long long old_key = L.best.inst != 0xFFFFFFFFu
+                                                 ? ((unsigned long long)(L.best.inst & kInstMask) << 32) | (L.best.inst & ~kInstMask) | L.best.prim
+                                                 : ~0ull;
+          const uint32_t old_t = __float_as_uint(L.tmax);
+          P.best_t[lane] = old_t, P.best_key[lane] = old_key, P.done[lane] = 0u;
+          __syncwarp();
+          float t = 0.f, b1 = 0.f, b2 = 0.f;
+          bool cand = false;
+          unsigned long long key = ~0ull;
+          if (have) {
+            if (COUNT) n_tris++;
+            atomicAdd(&P.done[src], 1u);
+            cand = hit_triangle(rs, f3(v0), f3(v1), f3(v2), t, b1, b2) && t > src_tmin && t <= src_tmax;
+            if (cand) {
+              const uint32_t pk = __float_as_uint(v1.w);  // kind << 28 | instance
+              key = ((unsigned long long)(pk & kInstMask) << 32) | (pk & ~kInstMask) | __float_as_uint(v0.w);
+              atomicMin(&P.best_t[src], __float_as_uint(t));
+            }
+          }
+          __syncwarp();
+          if (P.best_t[lane] < old_t) P.best_key[lane] = ~0ull;  // strictly nearer: the old hit no longer competes
+          __syncwarp();
+          cand = cand && __float_as_uint(t) == P.best_t[src];
+          if (cand) atomicMin(&P.best_key[src], key);
+          __syncwarp();
+          if (cand && key == P.best_key[src]) P.best_b1[src] = b1, P.best_b2[src] = b2;
+          __syncwarp();
+          const unsigned long long new_key = P.best_key[lane];
+          if (new_key != old_key) {
+            L.tmax = L.best.t = __uint_as_float(P.best_t[lane]);
+            L.best.b1 = P.best_b1[lane], L.best.b2 = P.best_b2[lane];
+            L.best.inst = (uint32_t)(new_key >> 32) | ((uint32_t)new_key & ~kInstMask);
+            L.best.prim = (uint32_t)new_key & 0x07FFFFFFu;
+          }
+          pending -= P.done[lane];
+          __syncwarp();
+          p_head = (p_head + nb) & (kPoolCap - 1), p_count -= nb;
+        }
+      }
+      if (!exhausted && (uint32_t)__popc(__ballot_sync(0xFFFFFFFFu, !staged)) >= sc.stage_lanes) break;
+    }
+  }
+  if (COUNT) {
+    for (int o = 16; o > 0; o >>= 1) {
+      n_nodes += __shfl_xor_sync(0xFFFFFFFFu, n_nodes, o);
+      n_tris += __shfl_xor_sync(0xFFFFFFFFu, n_tris, o);
+    }
+    if (lane == 0) {
+      atomicAdd(node_visits, (unsigned long long)n_nodes);
+      atomicAdd(tri_tests, (unsigned long long)n_tris);
+    }
+  }
+}
+
 }  // namespace asuna
