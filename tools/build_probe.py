@@ -15,5 +15,22 @@ ctx = capi.Context(gpu_id=0)
 ms = [sc.upload(ctx)]
 for _ in range(rep - 1):
     ms.append(ctx.build_accel())
+if ctx.L.has("debug_build_profile"):  # a -DASUNA_BUILD_PROFILE build: phase stamps of the LAST build
+    import ctypes
+    import numpy as np
+    buf = np.zeros((2048, 2), np.uint64)
+    k = ctx.L.fn("debug_build_profile")(buf.ctypes.data_as(ctypes.c_void_p), 2048)
+    buf = buf[:k]
+    # the reader drains the log: keep the stamps of the last build only (tag 1 = PLOC start)
+    tags, vals, t = (buf[:, 1] >> np.uint64(32)).astype(int), (buf[:, 1] & np.uint64(0xFFFFFFFF)).astype(int), buf[:, 0].astype(np.int64)
+    starts = np.flatnonzero(tags == 1)
+    start = int(starts[vals[starts] == vals[starts].max()][-1])  # the largest BVH of the last build
+    while start > 0 and tags[start - 1] >= 20 and t[start] - t[start - 1] < 500000:  # ... from its first kernel on
+        start -= 1
+    k = next((int(x) for x in np.flatnonzero(tags == 28) if x > start), k - 1) + 1
+    names = {1: "ploc init", 5: "tail start", 2: "nn", 3: "flags+scan", 4: "merge", 8: "emit init", 9: "emit level", 10: "emit prims", 20: "K world", 21: "K morton", 22: "K hist", 23: "K scan", 24: "K scatter", 25: "K ploc", 26: "K tail", 27: "K emit", 28: "end"}
+    for i in range(start, k):
+        dt = (t[i] - t[i - 1]) / 1e3 if i > start else 0.0
+        print(f"{names[tags[i]]:12s} {vals[i]:9d} {dt:9.1f} us", file=sys.stderr)
 print(json.dumps({"scene": which, "triangles": int(sum(len(sc.meshes[m][1]) // 3 for _, m, _, _ in sc.instances)), "build_ms": ms,
                   "accel": ctx.accel_stats()}))
