@@ -61,8 +61,15 @@ __global__ void k_bounds_init(int* bounds) {
   else if (threadIdx.x < 6) bounds[threadIdx.x] = (int)0x80000000;  // max = most negative ordered
 }
 
-__device__ __forceinline__ void reduce_bounds(float3 lo, float3 hi, bool valid, int* bounds) {
-  // centroid bounds: warp shuffle reduce, one atomic per warp
+// Centroid bounds of the primitives: warp shuffle reduce, then atomics only where they would still move the bound.  Six
+// same-line atomics from every one of the million warps of a 32 M-triangle build serialise in one L2 slice (measured:
+// 4.6 ms of a 28 ms build), and so do six volatile reads per warp (2.3 ms): each BLOCK reads the current bounds once
+// (snapshot, at the top of the kernel so the latency hides behind the vertex loads) and its warps compare against that
+// copy -- after the first few thousand blocks almost nothing improves the bounds any more.
+__device__ __forceinline__ void bounds_snapshot(int* snap, const int* bounds) {
+  if (threadIdx.x < 6) snap[threadIdx.x] = reinterpret_cast<const volatile int*>(bounds)[threadIdx.x];
+}
+__device__ __forceinline__ void reduce_bounds(float3 lo, float3 hi, bool valid, int* bounds, const int* snap) {
   float3 c = make_float3(0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z));
   float mnx = valid ? c.x : FLT_MAX, mny = valid ? c.y : FLT_MAX, mnz = valid ? c.z : FLT_MAX;
   float mxx = valid ? c.x : -FLT_MAX, mxy = valid ? c.y : -FLT_MAX, mxz = valid ? c.z : -FLT_MAX;
@@ -75,24 +82,23 @@ __device__ __forceinline__ void reduce_bounds(float3 lo, float3 hi, bool valid, 
     mxy = fmaxf(mxy, __shfl_xor_sync(0xFFFFFFFFu, mxy, o));
     mxz = fmaxf(mxz, __shfl_xor_sync(0xFFFFFFFFu, mxz, o));
   }
-  // One atomic per warp only where it would still move the bound: six same-line atomics from every one of the million
-  // warps of a 32 M-triangle build serialise in one L2 slice (measured: 4.6 ms of a 28 ms build); the plain read is cheap
-  // and after the first few thousand warps almost nothing improves the bounds any more.
+  __syncthreads();  // the snapshot is in shared memory
   if ((threadIdx.x & 31) == 0) {
-    const volatile int* b = bounds;
     const int o0 = float_to_ordered(mnx), o1 = float_to_ordered(mny), o2 = float_to_ordered(mnz);
     const int o3 = float_to_ordered(mxx), o4 = float_to_ordered(mxy), o5 = float_to_ordered(mxz);
-    if (o0 < b[0]) atomicMin(&bounds[0], o0);
-    if (o1 < b[1]) atomicMin(&bounds[1], o1);
-    if (o2 < b[2]) atomicMin(&bounds[2], o2);
-    if (o3 > b[3]) atomicMax(&bounds[3], o3);
-    if (o4 > b[4]) atomicMax(&bounds[4], o4);
-    if (o5 > b[5]) atomicMax(&bounds[5], o5);
+    if (o0 < snap[0]) atomicMin(&bounds[0], o0);
+    if (o1 < snap[1]) atomicMin(&bounds[1], o1);
+    if (o2 < snap[2]) atomicMin(&bounds[2], o2);
+    if (o3 > snap[3]) atomicMax(&bounds[3], o3);
+    if (o4 > snap[4]) atomicMax(&bounds[4], o4);
+    if (o5 > snap[5]) atomicMax(&bounds[5], o5);
   }
 }
 
 __global__ void k_tri_boxes(const AsunaVertex* __restrict__ v, const uint32_t* __restrict__ idx, uint32_t n,
                             float4* __restrict__ blo, float4* __restrict__ bhi, int* bounds) {
+  __shared__ int snap[6];
+  bounds_snapshot(snap, bounds);
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = i < n;
   float3 lo = make_float3(0, 0, 0), hi = lo;
@@ -107,7 +113,7 @@ __global__ void k_tri_boxes(const AsunaVertex* __restrict__ v, const uint32_t* _
     blo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
     bhi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
   }
-  reduce_bounds(lo, hi, valid, bounds);
+  reduce_bounds(lo, hi, valid, bounds, snap);
 }
 
 // Triangles of a single-use instance taken to world space once, at build time: the merged world-space BLAS
@@ -125,6 +131,8 @@ __global__ void __launch_bounds__(kThreads) k_world_triangles_batched(const Worl
   const WorldJob job = jobs[blockIdx.y];
   PROF(20, 0);
   if (blockIdx.x * kThreads >= job.n) return;  // whole block idle: no barrier or ballot is skipped by part of a warp
+  __shared__ int snap[6];
+  bounds_snapshot(snap, bounds);
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = i < job.n;
   float3 lo = make_float3(0, 0, 0), hi = lo;
@@ -144,13 +152,15 @@ __global__ void __launch_bounds__(kThreads) k_world_triangles_batched(const Worl
     blo[o] = make_float4(lo.x, lo.y, lo.z, 0.f);
     bhi[o] = make_float4(hi.x, hi.y, hi.z, 0.f);
   }
-  reduce_bounds(lo, hi, valid, bounds);
+  reduce_bounds(lo, hi, valid, bounds, snap);
 }
 
 // World box of an instance = box of the 8 transformed corners of its mesh box (what a TLAS build sees).
 __global__ void k_instance_boxes(const DInstance* __restrict__ inst, const uint32_t* __restrict__ ids,
                                  const float4* __restrict__ mesh_lo, const float4* __restrict__ mesh_hi, uint32_t n,
                                  float4* __restrict__ blo, float4* __restrict__ bhi, int* bounds) {
+  __shared__ int snap[6];
+  bounds_snapshot(snap, bounds);
   uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   bool valid = i < n;
   float3 lo = make_float3(0, 0, 0), hi = lo;
@@ -171,7 +181,7 @@ __global__ void k_instance_boxes(const DInstance* __restrict__ inst, const uint3
     blo[i] = make_float4(lo.x, lo.y, lo.z, 0.f);
     bhi[i] = make_float4(hi.x, hi.y, hi.z, 0.f);
   }
-  reduce_bounds(lo, hi, valid, bounds);
+  reduce_bounds(lo, hi, valid, bounds, snap);
 }
 
 // ---- 2. Morton keys -----------------------------------------------------------------------
@@ -430,10 +440,16 @@ __device__ __forceinline__ float union_half_area(float4 alo, float4 ahi, float4 
 //   C(n,1) = min( leaf: A P c_prim  if P <= 3 ,  inner: A c_node + min_k C(l,k) + C(r,8-k) )
 //   C(n,i) = min( min_k C(l,k) + C(r,i-k) , C(n,i-1) )          i = 2..7
 // dec: bit 0 = "C(n,1) is a leaf"; 6 bits per i = 2..8 at 4 + 6 (i-2): (k_left, k_right), 0 = the node itself.
-__device__ void dp_merge(const PlocParams& a, int idx, int l, int r, float area, uint32_t count) {
+// The row of a binary leaf is seven times (its area x c_prim); it is never stored, the merge that consumes it gets the
+// value from the box it holds anyway (a 32.8 M-triangle build saved 1.2 GB of writes and as many scattered reads).
+__device__ void dp_merge(const PlocParams& a, int idx, int l, int r, float area, uint32_t count, float leaf_l, float leaf_r) {
   float cl[7], cr[7], c[7];
+  const bool is_leaf_l = l >= a.n - 1, is_leaf_r = r >= a.n - 1;
 #pragma unroll
-  for (int i = 0; i < 7; i++) cl[i] = a.cost[(size_t)l * 7 + i], cr[i] = a.cost[(size_t)r * 7 + i];
+  for (int i = 0; i < 7; i++) {
+    cl[i] = is_leaf_l ? leaf_l : a.cost[(size_t)l * 7 + i];
+    cr[i] = is_leaf_r ? leaf_r : a.cost[(size_t)r * 7 + i];
+  }
   float best8 = FLT_MAX;
   uint32_t k8 = 1;
 #pragma unroll
@@ -487,7 +503,8 @@ __device__ __forceinline__ uint32_t block_scan_excl(uint32_t v, uint32_t& total,
   return before + s - v;
 }
 
-// The leaf clusters of the build: binary node n-1+j for sorted position j, with its collapse-table row.
+// The leaf clusters of the build: binary node n-1+j for sorted position j.  Only the box is stored (its collapse-table row
+// is synthesised by dp_merge, its decision word is never read); a one-primitive BVH has no merge, so its row is written.
 __device__ __forceinline__ void ploc_leaf(const PlocParams& a, int j, float4& lo, float4& hi, int& node) {
   const uint32_t prim = a.order[j];
   lo = a.blo[prim], hi = a.bhi[prim];
@@ -496,22 +513,27 @@ __device__ __forceinline__ void ploc_leaf(const PlocParams& a, int j, float4& lo
   node = a.n - 1 + j;
   a.nlo[node] = lo;
   a.nhi[node] = hi;
-  const float c = half_area(lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) * a.cost_prim;
+  if (a.n == 1) {
+    const float c = half_area(lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) * a.cost_prim;
 #pragma unroll
-  for (int i = 0; i < 7; i++) a.cost[(size_t)node * 7 + i] = c;
-  a.dec[node] = kDecLeaf;
+    for (int i = 0; i < 7; i++) a.cost[(size_t)node * 7 + i] = c;
+    a.dec[node] = kDecLeaf;
+  }
 }
 
 // The new inner node of a merge (numbered `idx`), its box and collapse-table row; returns the merged cluster.
 __device__ __forceinline__ void ploc_merge(const PlocParams& a, int idx, float4& lo, float4& hi, int& id, float4 lo2, float4 hi2,
                                            int id2) {
   const uint32_t count = __float_as_uint(lo.w) + __float_as_uint(lo2.w);
+  const float leaf_l = half_area(lo.x, hi.x, lo.y, hi.y, lo.z, hi.z) * a.cost_prim;
+  const float leaf_r = half_area(lo2.x, hi2.x, lo2.y, hi2.y, lo2.z, hi2.z) * a.cost_prim;
+  const int id1 = id;
   lo = make_float4(fminf(lo.x, lo2.x), fminf(lo.y, lo2.y), fminf(lo.z, lo2.z), __uint_as_float(count));
   hi = make_float4(fmaxf(hi.x, hi2.x), fmaxf(hi.y, hi2.y), fmaxf(hi.z, hi2.z), 0.f);
   a.children[idx] = make_int2(id, id2);
   a.nlo[idx] = lo;
   a.nhi[idx] = hi;
-  dp_merge(a, idx, id, id2, half_area(lo.x, hi.x, lo.y, hi.y, lo.z, hi.z), count);
+  dp_merge(a, idx, id1, id2, half_area(lo.x, hi.x, lo.y, hi.y, lo.z, hi.z), count, leaf_l, leaf_r);
   id = idx;
 }
 
@@ -542,18 +564,16 @@ __global__ void __launch_bounds__(kThreads, ASUNA_PLOC_MIN_BLOCKS) k_ploc(const 
     float4 lo, hi;
     int node;
     ploc_leaf(a, (int)j, lo, hi, node);
-    a.cid[0][j] = node;
-    a.clo[0][j] = lo;
-    a.chi[0][j] = hi;
   }
   grid.sync();
   PROF(1, n);
   int m = n, cur = 0, next_inner = n - 2;
   const uint32_t nb = gridDim.x, bid = blockIdx.x;
+  bool first = true;  // the clusters of the first round are the leaves themselves: boxes nlo / nhi[n-1 ..), ids n-1+i
   while (m > kPlocTail) {
-    const int* cid = a.cid[cur];
-    const float4* clo = a.clo[cur];
-    const float4* chi = a.chi[cur];
+    const int* cid = first ? nullptr : a.cid[cur];
+    const float4* clo = first ? a.nlo + (n - 1) : a.clo[cur];
+    const float4* chi = first ? a.nhi + (n - 1) : a.chi[cur];
     const int chunk = (m + (int)nb - 1) / (int)nb;
     const int c0 = min(m, (int)bid * chunk), c1 = min(m, c0 + chunk);
     // ---- A: nearest neighbours, merge flags, prefix inside the chunk
@@ -652,8 +672,8 @@ __global__ void __launch_bounds__(kThreads, ASUNA_PLOC_MIN_BLOCKS) k_ploc(const 
       if (mutual && i > j) continue;
       const uint2 pr = a.pre[i];
       float4 lo = clo[i], hi = chi[i];
-      int id = cid[i];
-      if (mutual) ploc_merge(a, next_inner - (int)(base_lead + pr.y), lo, hi, id, clo[j], chi[j], cid[j]);
+      int id = cid ? cid[i] : n - 1 + i;
+      if (mutual) ploc_merge(a, next_inner - (int)(base_lead + pr.y), lo, hi, id, clo[j], chi[j], cid ? cid[j] : n - 1 + j);
       const uint32_t pos = base_valid + pr.x;
       ocid[pos] = id;
       oclo[pos] = lo;
@@ -664,6 +684,7 @@ __global__ void __launch_bounds__(kThreads, ASUNA_PLOC_MIN_BLOCKS) k_ploc(const 
     m = (int)tot_valid;
     next_inner -= (int)tot_lead;
     cur ^= 1;
+    first = false;
   }
   if (gtid == 0) a.state[0] = m, a.state[1] = cur, a.state[2] = next_inner;
 }

@@ -103,6 +103,28 @@ def test_instanced_field_config3_reduced_film(gpu_ctx, ref_ctx):
     check(sc, gpu_ctx, ref_ctx)
 
 
+def test_multi_shot_sweep_config4(gpu_ctx, ref_ctx):
+    """BASELINE configs[4] at 1080p: the 16-shot thin-lens orbit of tools/run_configs.py (three of its shots, 2 spp each,
+    one with a per-shot spp / depth override) and an opencv pinhole shot, radiance + albedo / normal / depth AOVs against
+    the reference shaders.  The thin lens draws two more random numbers per sample (rgen:64-100): ids are compared on the
+    pinhole shot, where frame 0 has no jitter."""
+    sc = scenes.cornell(1920, 1080, spp=2, depth=5)
+    sc.camera["aperture"], sc.camera["focal_distance"] = 0.05, 3.0
+    scenes.orbit_shots(sc, 16, (0.5, 0.5, 0.5), 2.2, 0.5)
+    sc.shots[11].state = sc.state.copy()
+    sc.shots[11].state["spp"], sc.shots[11].state["maxPathDepth"] = 3, 2
+    sc.upload(gpu_ctx), sc.upload(ref_ctx)
+    for shot in (0, 5, 11):
+        g, c = sc.render_shot(gpu_ctx, shot), sc.render_shot(ref_ctx, shot)
+        assert metrics.mean_relative_error(g[0], c[0]) <= 0.01 and metrics.flip(g[0], c[0]) <= 0.01, shot
+        for k in range(1, len(g)):  # AOVs of a lens-sampled primary ray: a few pixels straddle an edge differently
+            d = np.abs(g[k][..., :3] - c[k][..., :3]).max(axis=2)
+            assert (d > 1e-4 * max(1.0, float(np.abs(c[k][..., :3]).max()))).mean() <= 1e-3, (shot, k)
+    so = scenes.cornell(1920, 1080, spp=2, depth=5)
+    so.set_camera("opencv", 1920, 1080, fxfycxcy=[1700.0, 1700.0, 960.0, 540.0])
+    check(so, gpu_ctx, ref_ctx)
+
+
 def test_frame_batches_beyond_one_internal_batch(gpu_ctx, ref_ctx):
     """24 frames of a 320x180 film = 3 internal batches of 8: the accumulation across batches against 24 reference
     frames (rgen:171-178)."""

@@ -25,7 +25,9 @@ if ctx.L.has("debug_build_profile"):  # a -DASUNA_BUILD_PROFILE build: phase sta
     tags, vals, t = (buf[:, 1] >> np.uint64(32)).astype(int), (buf[:, 1] & np.uint64(0xFFFFFFFF)).astype(int), buf[:, 0].astype(np.int64)
     starts = np.flatnonzero(tags == 1)
     start = int(starts[vals[starts] == vals[starts].max()][-1])  # the largest BVH of the last build
-    while start > 0 and tags[start - 1] >= 20 and t[start] - t[start - 1] < 500000:  # ... from its first kernel on
+    first = [int(x) for x in np.flatnonzero((tags == 20) | (tags == 21)) if x < start]  # ... from its first kernel on
+    start = first[-1] if first else start
+    while start > 0 and tags[start - 1] == 20:
         start -= 1
     k = next((int(x) for x in np.flatnonzero(tags == 28) if x > start), k - 1) + 1
     names = {1: "ploc init", 5: "tail start", 2: "nn", 3: "flags+scan", 4: "merge", 8: "emit init", 9: "emit level", 10: "emit prims", 20: "K world", 21: "K morton", 22: "K hist", 23: "K scan", 24: "K scatter", 25: "K ploc", 26: "K tail", 27: "K emit", 28: "end"}
