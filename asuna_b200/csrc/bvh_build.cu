@@ -28,8 +28,14 @@ namespace asuna {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSortItems = 16;
-constexpr int kSortTile = kThreads * kSortItems;  // 4096 keys per block
+#ifndef ASUNA_SORT_ITEMS
+#define ASUNA_SORT_ITEMS 16
+#endif
+#ifndef ASUNA_SORT_MIN_BLOCKS
+#define ASUNA_SORT_MIN_BLOCKS 3
+#endif
+constexpr int kSortItems = ASUNA_SORT_ITEMS;
+constexpr int kSortTile = kThreads * kSortItems;  // keys per block
 
 // Developer instrumentation (-DASUNA_BUILD_PROFILE, tools/build_probe.py): block 0 stamps the global timer at the phase
 // boundaries of the two cooperative kernels.
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_scan_rows(uint32_t* __restric
 // the number of L2 write transactions, not by bytes.
 constexpr size_t kScatterSmemBytes = (size_t)kSortTile * (sizeof(uint64_t) + sizeof(uint32_t));
 // (3 blocks per SM: the 320 blocks of a 1.3 M-key pass are then co-resident instead of leaving 24 for a second wave)
-__global__ void __launch_bounds__(kThreads, 3) k_sort_scatter(const uint64_t* __restrict__ keys_in,
+__global__ void __launch_bounds__(kThreads, ASUNA_SORT_MIN_BLOCKS) k_sort_scatter(const uint64_t* __restrict__ keys_in,
                                                             const uint32_t* __restrict__ vals_in,
                                                             uint64_t* __restrict__ keys_out,
                                                             uint32_t* __restrict__ vals_out, uint32_t n, int shift,
@@ -1082,6 +1088,9 @@ __device__ void emit_wide_node(const EmitParams& a, uint32_t w, bool valid, uint
 // Two builds of the same kernel: MIN_BLOCKS = 2 keeps the unrolled per-child state in registers and is faster up to a
 // few million primitives, where a level's barrier waits for the slowest thread; MIN_BLOCKS = 4 (64 registers, twice the
 // resident warps) is for the builds that are throughput-bound.
+#ifndef ASUNA_EMIT_BIG_BLOCKS
+#define ASUNA_EMIT_BIG_BLOCKS 4
+#endif
 template <int MIN_BLOCKS>
 __global__ void __launch_bounds__(kThreads, MIN_BLOCKS) k_emit_wide(const EmitParams a) {
   cg::grid_group grid = cg::this_grid();
@@ -1161,7 +1170,7 @@ cudaError_t BuildScratch::reserve(uint32_t n) {
     if ((e = cudaFuncSetAttribute(k_ploc_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTailSmemBytes)) != cudaSuccess) return e;
     if ((e = cudaFuncSetAttribute(k_sort_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmemBytes)) != cudaSuccess) return e;
     int per_sm_c = 0;
-    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_emit_wide<4>, kThreads, 0)) != cudaSuccess) return e;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_b, k_emit_wide<ASUNA_EMIT_BIG_BLOCKS>, kThreads, 0)) != cudaSuccess) return e;
     if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_c, k_emit_wide<2>, kThreads, 0)) != cudaSuccess) return e;
     // each cooperative kernel gets the largest co-resident grid IT fits: both walk trees through dependent, scattered
     // loads, so resident warps are what hides their latency (ASUNA_BUILD_BLOCKS_PER_SM caps both, for experiments)
@@ -1297,7 +1306,7 @@ cudaError_t launch_build_wide(cudaStream_t s, uint32_t n, WideNode* nodes, uint3
   void* eargs[] = {&ep};
   const bool small = n <= (4u << 20);
   const uint32_t grid_emit = std::max(1u, std::min(small ? sc.coop_blocks_emit_small : sc.coop_blocks_emit, div_up(n, kThreads)));
-  return cudaLaunchCooperativeKernel(small ? (const void*)k_emit_wide<2> : (const void*)k_emit_wide<4>, dim3(grid_emit),
+  return cudaLaunchCooperativeKernel(small ? (const void*)k_emit_wide<2> : (const void*)k_emit_wide<ASUNA_EMIT_BIG_BLOCKS>, dim3(grid_emit),
                                      dim3(kThreads), eargs, 0, s);
 }
 
