@@ -21,7 +21,7 @@ PRODUCT_LIB = os.environ.get("ASUNA_B200_LIB") or os.path.join(_HERE, "libasuna_
 ABI_SYMBOLS = (
     "abi_sizes", "create", "destroy", "last_error", "set_film", "add_texture", "set_envmap", "add_mesh",
     "add_material", "set_lights", "add_instance", "build_accel", "set_camera", "set_sunsky", "set_state",
-    "reset_frame", "render_frames", "set_partition", "sync", "read_channel", "export_partial",
+    "reset_frame", "render_frames", "set_partition", "sync", "read_channel", "read_channel_async", "wait_reads", "export_partial",
     "import_partial", "post_process", "host_alloc", "host_free", "channel_device_ptr", "stream_handle", "set_counting", "set_profiling", "get_stats", "reset_stats", "trace_primary", "trace_rays",
     "occlusion_rays", "accel_stats")
 
@@ -168,6 +168,15 @@ class Context:
         assert out.dtype == np.float32 and out.size == self.height * self.width * 4 and out.flags.c_contiguous
         self._call("read_channel", C.c_int(ch), _ptr(out))
         return out
+
+    def read_channel_async(self, ch, out):
+        """Queues the read of image `ch` into the page-locked array `out` (pinned_image()) and returns at once; `out` is
+        valid after wait_reads()."""
+        assert out.dtype == np.float32 and out.size == self.height * self.width * 4 and out.flags.c_contiguous
+        self._call("read_channel_async", C.c_int(ch), _ptr(out))
+
+    def wait_reads(self):
+        self._call("wait_reads")
 
     def post_process(self, post):
         """Tone-mapped radiance image, (h, w, 4) float32 (≙ PipelinePost::run + offline colour read-back)."""

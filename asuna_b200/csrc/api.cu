@@ -115,6 +115,13 @@ struct asuna_ctx {
   void* path_arena = nullptr;   // the whole wavefront state: one allocation
   void* scene_arena = nullptr;  // nodes, triangle slots and the flat scene tables: one allocation per build
   cudaStream_t upload_stream = nullptr;  // H2D copies of textures / env tables / meshes overlap the BVH build
+  // asuna_read_channel_async: the image is snapshotted into d_readback on `stream`, the D2H copy of the snapshot runs on
+  // read_stream while later work on `stream` proceeds
+  cudaStream_t read_stream = nullptr;
+  cudaEvent_t ev_read_ready = nullptr, ev_read_done = nullptr;
+  float4* d_readback = nullptr;
+  size_t readback_px = 0;
+  bool read_pending = false;
   cudaEvent_t ev_geometry = nullptr, ev_textures = nullptr, ev_partial = nullptr;
   bool textures_pending = false;
 
@@ -388,9 +395,10 @@ void asuna_destroy(asuna_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->upload_stream) cudaStreamSynchronize(ctx->upload_stream);
+  if (ctx->read_stream) cudaStreamSynchronize(ctx->read_stream);
   collect_timers(ctx);
   for (auto e : ctx->event_pool) cudaEventDestroy(e);
-  for (cudaEvent_t e : {ctx->ev_geometry, ctx->ev_textures, ctx->ev_partial})
+  for (cudaEvent_t e : {ctx->ev_geometry, ctx->ev_textures, ctx->ev_partial, ctx->ev_read_ready, ctx->ev_read_done})
     if (e) cudaEventDestroy(e);
   free_scene_device(ctx);
   free_path_buffers(ctx);
@@ -412,6 +420,8 @@ void asuna_destroy(asuna_ctx* ctx) {
   ctx->scratch.release();
   cudaStreamDestroy(ctx->stream);
   if (ctx->upload_stream) cudaStreamDestroy(ctx->upload_stream);
+  if (ctx->read_stream) cudaStreamDestroy(ctx->read_stream);
+  free_dev(ctx->d_readback);
   delete ctx;
 }
 
@@ -922,6 +932,41 @@ int asuna_read_channel(asuna_ctx* ctx, int ch, float* out) {
   ASUNA_CUDA_CHECK(cudaMemcpyAsync(out, ctx->out.img[ch], (size_t)ctx->W * ctx->H * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
   ASUNA_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
   collect_timers(ctx);
+  return 0;
+}
+
+int asuna_read_channel_async(asuna_ctx* ctx, int ch, float* out) {
+  NvtxRange nvtx("asuna_read_channel_async");
+  if (ch < 0 || ch >= ASUNA_NUM_OUTPUT_IMAGES || !out) return fail(ctx, ASUNA_E_INVALID, "bad channel");
+  if (ctx->W == 0) return fail(ctx, ASUNA_E_INVALID, "asuna_set_film not called");
+  cudaSetDevice(ctx->device);
+  const size_t px = (size_t)ctx->W * ctx->H;
+  if (!ctx->read_stream) {
+    ASUNA_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->read_stream, cudaStreamNonBlocking));
+    ASUNA_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_read_ready, cudaEventDisableTiming));
+    ASUNA_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_read_done, cudaEventDisableTiming));
+  }
+  if (ctx->readback_px < px) {
+    if (ctx->read_pending) ASUNA_CUDA_CHECK(cudaEventSynchronize(ctx->ev_read_done));
+    free_dev(ctx->d_readback);
+    ctx->readback_px = 0;
+    ASUNA_CUDA_CHECK(cudaMalloc(&ctx->d_readback, px * sizeof(float4)));
+    ctx->readback_px = px;
+  }
+  // the snapshot buffer is free again once the previous copy out of it has finished (a stream-side wait, not a host one)
+  if (ctx->read_pending) ASUNA_CUDA_CHECK(cudaStreamWaitEvent(ctx->stream, ctx->ev_read_done, 0));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(ctx->d_readback, ctx->out.img[ch], px * sizeof(float4), cudaMemcpyDeviceToDevice, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaEventRecord(ctx->ev_read_ready, ctx->stream));
+  ASUNA_CUDA_CHECK(cudaStreamWaitEvent(ctx->read_stream, ctx->ev_read_ready, 0));
+  ASUNA_CUDA_CHECK(cudaMemcpyAsync(out, ctx->d_readback, px * sizeof(float4), cudaMemcpyDeviceToHost, ctx->read_stream));
+  ASUNA_CUDA_CHECK(cudaEventRecord(ctx->ev_read_done, ctx->read_stream));
+  ctx->read_pending = true;
+  return 0;
+}
+int asuna_wait_reads(asuna_ctx* ctx) {
+  cudaSetDevice(ctx->device);
+  if (ctx->read_pending) ASUNA_CUDA_CHECK(cudaEventSynchronize(ctx->ev_read_done));
+  ctx->read_pending = false;
   return 0;
 }
 

@@ -15,7 +15,9 @@ rank 0 with one NCCL reduce and resolved there.
             synchronize, CUDA events on the library's stream, max over ranks (+ the one NCCL reduce at N>1).
 `e2e`     : the same metric through the reference-facing C ABI with HOST buffers: every step uploads the
             step's camera / state / sun-sky structs from host memory, renders, resolves (NCCL reduce at
-            N > 1) and reads the radiance image back into host memory (a complete mini-shot).
+            N > 1) and reads the radiance image back into page-locked host memory (a complete mini-shot); the copy
+            of step k runs on the library's read stream while step k + 1 renders (asuna_read_channel_async) and
+            the last one is awaited before the clock stops.
 `roofline`: closest-hit trace kernel (dominant): algorithmic bytes per ray (32 B ray in +
             16 B hit out + visited nodes x 80 B + tested triangles x 48 B, counts from an untimed
             instrumented pass over the same BVH) x rays per launch / mean launch time (CUDA events).  The contract's
@@ -309,7 +311,9 @@ def main():
     cam_host = sc.gpu_camera(sc.shots[0])
     h2d = cam_host.nbytes + sc.shot_state(0).nbytes + sc.sunsky.nbytes
     d2h = n_px * 16
-    img = ctx.pinned_image() if rank == 0 else None  # page-locked read-back buffer (asuna_host_alloc), reused every step
+    # two page-locked read-back buffers (asuna_host_alloc), used in turn: the copy of step k travels on the context's
+    # read stream while step k + 1 renders (asuna_read_channel_async); the last one is awaited inside the timed region
+    imgs = [ctx.pinned_image(), ctx.pinned_image()] if rank == 0 else None
     ctx.set_profiling(False)  # what an integration gets by default: no per-launch event records
     for _ in range(2):
         sc.begin_shot(ctx, 0)
@@ -317,12 +321,15 @@ def main():
         resolve()
     barrier()
     e0 = time.perf_counter()
-    for _ in range(args.steps):
+    for k in range(args.steps):
         sc.begin_shot(ctx, 0)  # camera + state + sun/sky structs from host memory
         ctx.render_frames(global_frames_per_step)
         resolve()
         if rank == 0:
-            ctx.read_channel(0, out=img)  # radiance image back into (pinned) host memory
+            ctx.read_channel_async(0, imgs[k & 1])  # radiance image back into (pinned) host memory
+    if rank == 0:
+        ctx.wait_reads()
+    ctx.sync()
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - e0)
     t = torch.tensor([e2e_ms], device=dev, dtype=torch.float64)

@@ -264,6 +264,14 @@ int asuna_sync(asuna_ctx* ctx);
 /* ≙ vkTextureToBuffer + map, reference src/tracer/tracer.cpp:313-342,365.
  * channel 0 = radiance mean, 1..7 = AOVs (frame 0), 8 = filter-weight sum.  w*h*4 floats. */
 int asuna_read_channel(asuna_ctx* ctx, int channel, float* rgba32f_out);
+/* The same read without stalling the context: the image is snapshotted on the context's stream (so later
+ * asuna_reset_frame / asuna_render_frames calls may overwrite it at once) and the snapshot travels to the host on a
+ * second stream while that later work runs -- the multi-shot loop of reference src/tracer/tracer.cpp:205-262 with the
+ * copy of shot k hidden behind the rendering of shot k+1.  `rgba32f_out` should be page-locked (asuna_host_alloc) and
+ * must not be read, written or freed before asuna_wait_reads returns; one read may be in flight per context, a second
+ * one queues behind it on the device. */
+int asuna_read_channel_async(asuna_ctx* ctx, int channel, float* rgba32f_out);
+int asuna_wait_reads(asuna_ctx* ctx);
 
 /* Page-locked host memory for the read-back / upload buffers of a caller (≙ the host-visible, host-coherent
  * staging buffer the reference maps in src/tracer/tracer.cpp:317-336): asuna_read_channel into such a buffer is

@@ -1780,6 +1780,8 @@ int oracle_read_channel(oracle_ctx* c, int ch, float* out) {
   std::memcpy(out, c->images[ch].data(), c->images[ch].size() * sizeof(float));
   return 0;
 }
+int oracle_read_channel_async(oracle_ctx* c, int ch, float* out) { return oracle_read_channel(c, ch, out); }  // nothing to overlap on the CPU
+int oracle_wait_reads(oracle_ctx*) { return 0; }
 // post.idle.frag:71-133 + utils/tonemapping.glsl over image 0 (≙ asuna_post_process).  In libref.so the fragment shader
 // itself runs (refglsl_post_process).
 int oracle_post_process(oracle_ctx* c, const AsunaPost* tm, float* out) {

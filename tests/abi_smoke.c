@@ -16,7 +16,7 @@ int main(void) {
   TAKE(asuna_abi_sizes); TAKE(asuna_create); TAKE(asuna_destroy); TAKE(asuna_last_error); TAKE(asuna_set_film);
   TAKE(asuna_add_texture); TAKE(asuna_set_envmap); TAKE(asuna_add_mesh); TAKE(asuna_add_material); TAKE(asuna_set_lights);
   TAKE(asuna_add_instance); TAKE(asuna_build_accel); TAKE(asuna_set_camera); TAKE(asuna_set_sunsky); TAKE(asuna_set_state);
-  TAKE(asuna_reset_frame); TAKE(asuna_render_frames); TAKE(asuna_set_partition); TAKE(asuna_sync); TAKE(asuna_read_channel);
+  TAKE(asuna_reset_frame); TAKE(asuna_render_frames); TAKE(asuna_set_partition); TAKE(asuna_sync); TAKE(asuna_read_channel); TAKE(asuna_read_channel_async); TAKE(asuna_wait_reads);
   TAKE(asuna_export_partial); TAKE(asuna_post_process); TAKE(asuna_import_partial); TAKE(asuna_host_alloc); TAKE(asuna_host_free);
   TAKE(asuna_channel_device_ptr); TAKE(asuna_stream_handle); TAKE(asuna_set_counting); TAKE(asuna_set_profiling);
   TAKE(asuna_get_stats); TAKE(asuna_reset_stats); TAKE(asuna_trace_primary); TAKE(asuna_trace_rays); TAKE(asuna_occlusion_rays);

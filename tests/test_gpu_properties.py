@@ -90,3 +90,29 @@ def test_small_film_batches_of_64_frames_equal_single_frames(product_lib):
     assert a.stats()["paths"] == 70 * 64 * 48
     for x in (a, b, c):
         x.close()
+
+
+def test_async_read_back_is_a_snapshot(product_lib):
+    """asuna_read_channel_async: the image is snapshotted on the context's stream, so the shot that is started right
+    after the call cannot leak into it, and two reads queued back to back land in their own buffers."""
+    sc = scenes.cornell_materials(256, 144, spp=4, depth=4, env=True, lights="rect", textured=True)
+    ctx = capi.Context(product_lib, 0)
+    sc.upload(ctx)
+    sc.begin_shot(ctx, 0)
+    ctx.render_frames(4)
+    want0 = ctx.read_channel(0).copy()
+    sc.begin_shot(ctx, 1 if len(sc.shots) > 1 else 0)
+    ctx.render_frames(2)
+    want1 = ctx.read_channel(0).copy()
+    a, b = ctx.pinned_image(), ctx.pinned_image()
+    a[:], b[:] = -1.0, -1.0
+    sc.begin_shot(ctx, 0)
+    ctx.render_frames(4)
+    ctx.read_channel_async(0, a)
+    sc.begin_shot(ctx, 1 if len(sc.shots) > 1 else 0)  # resets the film while the first copy may still be in flight
+    ctx.render_frames(2)
+    ctx.read_channel_async(0, b)
+    ctx.wait_reads()
+    assert np.array_equal(a, want0) and np.array_equal(b, want1)
+    assert not np.array_equal(want0, want1)
+    ctx.close()
