@@ -5,7 +5,7 @@ import ctypes as C
 import numpy as np
 import pytest
 
-from asuna_b200 import host, scenes
+from asuna_b200 import host, scenes, structs as S
 
 pytestmark = pytest.mark.gpu
 
@@ -216,6 +216,62 @@ def test_bvh_is_a_valid_tree(gpu_ctx, which):
     st = gpu_ctx.accel_stats()
     assert r["nodes_used"] == st["nodes"] and r["max_depth"] <= 24
     assert abs(r["sah"] / st["sah_cost"] - 1.0) <= 0.05, (r["sah"], st["sah_cost"])  # decoded boxes are a little larger
+
+
+def soup_scene(n, mode, seed=3):
+    """n small triangles: 'random' in the unit cube, 'line' with all centroids on one axis, 'same' all at one place
+    (every Morton key equal), 'two_clusters' far apart (empty space inside the root)."""
+    rng = np.random.RandomState(seed + n)
+    c = rng.rand(n, 3)
+    if mode == "line":
+        c[:, 1:] = 0.5
+    elif mode == "same":
+        c[:] = 0.5
+    elif mode == "two_clusters":
+        c = c * 0.01 + np.where(rng.rand(n, 1) < 0.5, 0.0, 100.0)
+    v = np.zeros(3 * n, S.Vertex)
+    v["pos"] = (c[:, None, :] + 0.02 * (rng.rand(n, 3, 3) - 0.5)).reshape(-1, 3)
+    v["normal"] = (0, 0, 1)
+    sc = scenes.Scene()
+    sc.set_camera("perspective", 16, 16)
+    sc.add_material("m", scenes.mat(0))
+    sc.add_mesh("soup", v, np.arange(3 * n, dtype=np.uint32))
+    sc.add_instance("soup", "m")
+    sc.shots.append(host.Shot((0.5, 0.5, 4), (0.5, 0.5, 0.5), (0, 1, 0)))
+    return sc, v["pos"].reshape(n, 3, 3).mean(axis=1).astype(np.float64)  # the triangles' centroids
+
+
+@pytest.mark.parametrize("n,mode", [(1, "random"), (2, "random"), (3, "random"), (4, "random"), (9, "random"), (33, "random"),
+                                    (255, "same"), (1000, "line"), (2047, "random"), (2048, "random"), (2049, "random"),
+                                    (2305, "two_clusters"), (4097, "random"), (70001, "random"), (70001, "same")])
+def test_builder_at_its_thresholds(gpu_ctx, cpu_ctx, n, mode):
+    """Primitive counts around every switch of the builder (one-primitive BVH, <= 3 primitives = a single leaf child,
+    the 2048-cluster hand-over from the grid rounds to the shared-memory tail, one / several sort tiles) and degenerate
+    placements (all Morton keys equal, collinear centroids, two far clusters): the tree is a valid tree over exactly the
+    n primitives, and rays aimed at the triangles find the same nearest hit as the oracle's BVH2."""
+    from helpers import download_accel, walk_wide_bvh
+    sc, c = soup_scene(n, mode)
+    sc.upload(gpu_ctx), sc.upload(cpu_ctx)
+    nodes, tris, root = download_accel(gpu_ctx)
+    r = walk_wide_bvh(nodes, tris, root)
+    assert len(tris) == n and (r["refs"] == 1).all() and r["outside"] == 0
+    assert sorted(tris["prim"].tolist()) == list(range(n))
+    st = gpu_ctx.accel_stats()
+    assert st["leaf_prims"] == n and r["nodes_used"] == st["nodes"]
+    rng = np.random.RandomState(n)
+    k = max(min(n, 4000), 64)
+    tgt = c[rng.randint(0, n, k)] + 0.0004 * (rng.rand(k, 3) - 0.5)
+    org = tgt + (rng.rand(k, 3) - 0.5) * (300.0 if mode == "two_clusters" else 3.0)
+    d = tgt - org
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = np.concatenate([org, np.zeros((k, 1)), d, np.full((k, 1), 1e30)], axis=1).astype(np.float32)
+    tg, ig = gpu_ctx.trace_rays(rays)
+    tc, ic = cpu_ctx.trace_rays(rays)
+    hit_g, hit_c = ig[:, 0] != 0xFFFFFFFF, ic[:, 0] != 0xFFFFFFFF
+    assert np.array_equal(hit_g, hit_c) and hit_c.mean() > 0.3
+    same = (ig == ic).all(axis=1)
+    tie = ~same & (np.abs(tg[:, 0] - tc[:, 0]) <= 1e-5 * np.maximum(1.0, np.abs(tc[:, 0])))  # same t, other primitive
+    assert (same | tie).mean() >= 0.999 and np.allclose(tg[same & hit_c, 0], tc[same & hit_c, 0], rtol=1e-5, atol=1e-6)
 
 
 def test_bvh_sah_quality_against_cpu_binned_sah(gpu_ctx, cpu_ctx, oracle_lib):
