@@ -5,7 +5,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 for tool in memcheck racecheck synccheck; do
-  for tgt in smoke two_level sort; do
+  for tgt in smoke two_level sort build; do
     out=gpurun_out/sanitize_${tool}_${tgt}.txt
     timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_targets.py $tgt > $out 2>&1
     echo "rc=$?" >> $out

@@ -3,6 +3,8 @@ in seconds under memcheck / racecheck.
   smoke      : 64x64 Cornell, 4 frames, depth 4 (flattened single-level kernels, shade kernels, accumulate)
   two_level  : instanced field with flattening off (instance-level traversal) + all twelve materials + env map
   sort       : the builder's radix sort on 100 k random 64-bit keys, checked against numpy
+  build      : a 9 k-triangle scene (PLOC grid rounds on shared-memory tiles, hand-over to the single-block tail, several
+               emit levels, two sort tiles per pass) + the asynchronous read-back
 """
 import ctypes as C
 import os
@@ -32,6 +34,20 @@ elif which == "two_level":
     print("materials mean", float(sc.render_shot(ctx, 0)[0][..., :3].mean()))
     ids, _ = ctx.trace_primary()
     print("primary hits", int((ids[..., 0] != 0xFFFFFFFF).sum()))
+elif which == "build":
+    sc = scenes.glass_blob(48, 32, spp=2, depth=4, subdiv=4, env_size=(16, 8))
+    sc.upload(ctx)
+    print("accel", ctx.accel_stats())
+    sc.begin_shot(ctx, 0)
+    ctx.render_frames(2)
+    a, b = ctx.pinned_image(), ctx.pinned_image()
+    ctx.read_channel_async(0, a)
+    sc.begin_shot(ctx, 0)
+    ctx.render_frames(2)
+    ctx.read_channel_async(0, b)
+    ctx.wait_reads()
+    assert np.array_equal(a, b)
+    print("build mean", float(a[..., :3].mean()))
 elif which == "sort":
     rng = np.random.RandomState(1)
     keys = rng.randint(0, 2 ** 63, 100000, dtype=np.int64).astype(np.uint64)
