@@ -173,6 +173,19 @@ def test_png_reader_and_writer(cli, tmp_path):
     _convert(cli, str(tmp_path / "f.npy"), str(tmp_path / "f.png"))
     back = np.asarray(Image.open(str(tmp_path / "f.png")))
     assert back.shape == (5, 6, 4) and np.array_equal(back, np.clip((f * 255 + 0.5).astype(np.int64), 0, 255).astype(np.uint8))
+    # a film-sized image: the IDAT stream is deflated in bands by several threads and must read as one zlib stream
+    # (PIL, cv2 and the repository's own reader), smooth content and noise alike
+    yy, xx = np.mgrid[0:540, 0:960].astype(np.float32)
+    big = np.stack([xx / 960, yy / 540, 0.5 + 0.5 * np.sin(xx * 0.05) * np.cos(yy * 0.03), np.ones_like(xx)], axis=2).astype(np.float32)
+    big[200:300, 300:500] = rng.rand(100, 200, 4)
+    np.save(str(tmp_path / "big.npy"), big)
+    _convert(cli, str(tmp_path / "big.npy"), str(tmp_path / "big.png"))
+    want = np.clip((big * 255 + 0.5).astype(np.int64), 0, 255).astype(np.uint8)
+    assert np.array_equal(np.asarray(Image.open(str(tmp_path / "big.png"))), want)
+    import cv2
+    assert np.array_equal(cv2.imread(str(tmp_path / "big.png"), cv2.IMREAD_UNCHANGED)[..., [2, 1, 0, 3]], want)
+    _convert(cli, str(tmp_path / "big.png"), str(tmp_path / "big_back.npy"))
+    assert np.allclose(np.load(str(tmp_path / "big_back.npy")), want / 255.0, atol=2e-7)
 
 
 def test_hdr_exr_pfm_round_trips(cli, tmp_path):
