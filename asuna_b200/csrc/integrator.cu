@@ -295,7 +295,8 @@ constexpr bool shade_kind_textured(uint32_t kind) {
 }
 template <uint32_t KIND>
 __global__ void __launch_bounds__(kShadeThreads, shade_kind_textured(KIND) ? ASUNA_SHADE_MIN_BLOCKS_TEXTURED : ASUNA_SHADE_MIN_BLOCKS)
-k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParams fp, PathState ps, OutputImages out, Counters* cnt, int iter,
+k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParams fp, const __grid_constant__ PathState ps,
+        const __grid_constant__ OutputImages out, Counters* cnt, int iter,
         int qsel, uint32_t n_blocks) {
   const uint32_t begin = ps.bin_hist[KIND * n_blocks];
   const uint32_t end = KIND + 1 < kNumKinds ? ps.bin_hist[(KIND + 1) * n_blocks] : cnt->queue[iter];
@@ -313,6 +314,7 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
   se.env.res_x = fp.pc.envMapResolution[0];
   se.env.res_y = fp.pc.envMapResolution[1];
   se.env.intensity = fp.pc.envMapIntensity;
+  se.out = &out;
 
   for (uint32_t base = begin + warp_global * 32; base < end; base += n_warps * 32) {
     uint32_t i = base + lane;
@@ -331,7 +333,7 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
       if constexpr (kRadiance) ra = ps.rad[slot];
       uint32_t fi = slot / fp.n_pixels, pixel = slot - fi * fp.n_pixels;
       bool frame0 = fp.frame_ids[fi] == 0;
-      for (int c = 0; c < ASUNA_NUM_OUTPUT_IMAGES - 1; c++) se.aov[c] = frame0 ? out.img[c + 1] : nullptr;
+      se.frame0 = frame0;
       p.ray_o = f3(ro), p.ray_d = f3(rd), p.throughput = f3(th), p.radiance = f3(ra);
       p.seed = __float_as_uint(ro.w);
       p.bsdf_pdf = rd.w;
@@ -344,13 +346,14 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
         shade_miss(se, p);
       } else {
         const uint4 hit = ps.hit[slot];
-        const DInstance in = sc.instances[hit.z];
+        const DInstance& in = sc.instances[hit.z];  // fields are fetched where they are used (L1-resident tables): a by-value
+                                                    // copy of the 128-byte record lives in local memory
         Surface s;
         load_surface(sc, fp.pc, in, hit, p.ray_d, s);
         if constexpr (KIND == kKindLight) {
           shade_light_hit(se, p, in.light, s.pos);
         } else {
-          const AsunaMaterial m = sc.materials[in.material];
+          const AsunaMaterial& m = sc.materials[in.material];
           constexpr uint32_t T = KIND - kKindMaterial0;
           if constexpr (T == ASUNA_MAT_LAMBERTIAN) shade_lambertian(se, p, s, m, pixel);
           else if constexpr (T == ASUNA_MAT_EMISSIVE) shade_emissive(se, p, s, m);

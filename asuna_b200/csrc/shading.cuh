@@ -475,7 +475,8 @@ struct ShadeEnv {  // read-only inputs of one shade call
   const SceneView* scene;
   const FrameParams* fp;
   EnvCtx env;
-  float4* aov[ASUNA_NUM_OUTPUT_IMAGES - 1];  // channel cid -> image cid+1 (frame 0 only), else null
+  const OutputImages* out;  // kernel parameter (constant bank): channel cid -> image cid + 1, written on frame 0 only
+  bool frame0;
 };
 
 ADEV void configure_frame(const AsunaState& pc, Surface& s) {  // rchit_layouts.glsl:61-65
@@ -616,7 +617,7 @@ ADEV float3 diffuse_of(const ShadeEnv& se, const AsunaMaterial& m, const Surface
   return m.diffuseTextureId >= 0 ? f3(tex(se, m.diffuseTextureId, s.uv)) : f3(m.diffuse);
 }
 ADEV void write_aov(const ShadeEnv& se, uint32_t pixel, int ch, float3 v) {
-  if (ch >= 0 && ch < ASUNA_NUM_OUTPUT_IMAGES - 1 && se.aov[ch]) se.aov[ch][pixel] = make_float4(v.x, v.y, v.z, 1.0f);
+  if (se.frame0 && ch >= 0 && ch < ASUNA_NUM_OUTPUT_IMAGES - 1) se.out->img[ch + 1][pixel] = make_float4(v.x, v.y, v.z, 1.0f);
 }
 
 // ---- microfacet pieces shared by pbr / rough_plastic / kang18 (identical text in the three shaders)
