@@ -280,14 +280,17 @@ __global__ void __launch_bounds__(256) k_bin_scatter(PathState ps, const Counter
 
 // ---- shading: one kernel per hit kind (≙ one closest-hit / miss shader each) -----------------------
 // Resident blocks per SM the shade kernels are compiled for.  They are latency-bound (dependent gathers: instance ->
-// indices -> vertices -> material -> texels), so occupancy beats register-resident state: 8 blocks (64 registers, the
-// rest in L1-resident local memory) is neutral for the texture-free shaders and +14 % on the textured PBR config; the
-// shaders that fetch up to five textures per hit (pbr, kang18, disney) keep gaining up to 12 blocks (+19 %).
+// indices -> vertices -> material -> texels), so occupancy competes with register-resident state, and what a capped
+// kernel spills is not free: local-memory lines of finished threads are dirty and travel to L2 / DRAM (ncu: 20 GB of
+// local sectors in one 16 M-path launch of the PBR shader at 40 registers, more than its path state and texels
+// together).  Round 1 (per-thread copies of the instance / material records and an AOV pointer array on the stack):
+// 8 blocks, 12 for the shaders that fetch up to five textures.  Round 2, with those stack objects gone: 6 blocks (80
+// registers) and 8 (64) -- measured 4 / 5 / 6 / 7 / 8 / 10 / 12 and 4 / 5 / 6 / 8 / 10 / 12 / 16 on C1 / C2 / C3 / C4.
 #ifndef ASUNA_SHADE_MIN_BLOCKS
-#define ASUNA_SHADE_MIN_BLOCKS 8
+#define ASUNA_SHADE_MIN_BLOCKS 6
 #endif
 #ifndef ASUNA_SHADE_MIN_BLOCKS_TEXTURED
-#define ASUNA_SHADE_MIN_BLOCKS_TEXTURED 12
+#define ASUNA_SHADE_MIN_BLOCKS_TEXTURED 8
 #endif
 constexpr bool shade_kind_textured(uint32_t kind) {
   return kind == kKindMaterial0 + ASUNA_MAT_PBR_METALNESS_ROUGHNESS || kind == kKindMaterial0 + ASUNA_MAT_KANG18 ||
