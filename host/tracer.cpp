@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <stdexcept>
 #include <thread>
 
@@ -58,6 +59,8 @@ void tonemap(const std::string& name, int n, const float* hdr, float* out) {
 }
 
 Tracer::~Tracer() {
+  for (auto& w : m_writers)
+    if (w.valid()) w.wait();
   for (void* c : m_comms)
     if (c) ncclCommDestroy((ncclComm_t)c);
   for (asuna_ctx* c : m_ctx)
@@ -149,11 +152,12 @@ std::vector<ShotReport> Tracer::run() {
         double t1 = now_ms();
         save_shot(rep.shot, g);
         rep.save_ms = now_ms() - t1;
-        fprintf(stderr, "[info] shot %04d on GPU %d: %d spp, group of %d shots in %.1f ms, saved in %.1f ms\n", rep.shot,
+        fprintf(stderr, "[info] shot %04d on GPU %d: %d spp, group of %d shots in %.1f ms, read back in %.1f ms (files are written in the background)\n", rep.shot,
                 m_tis.gpu_id + g, tot[g], cnt, render_ms, rep.save_ms);
         reports.push_back(rep);
       }
     }
+    drain_writers(0);
     return reports;
   }
   for (size_t shot = 0; shot < m_scene.shots.size(); shot++) {
@@ -190,10 +194,13 @@ std::vector<ShotReport> Tracer::run() {
     double t1 = now_ms();
     save_shot((int)shot);
     rep.save_ms = now_ms() - t1;
-    fprintf(stderr, "[info] shot %04d: %d spp in %.1f ms (%.1f M samples/s), saved in %.1f ms\n", (int)shot, tot, rep.render_ms,
+    fprintf(stderr, "[info] shot %04d: %d spp in %.1f ms (%.1f M samples/s), read back in %.1f ms (files are written in the background)\n", (int)shot, tot, rep.render_ms,
             (double)tot * m_scene.camera.width * m_scene.camera.height / rep.render_ms / 1e3, rep.save_ms);
     reports.push_back(rep);
   }
+  double tw = now_ms();
+  drain_writers(0);
+  if (!reports.empty()) fprintf(stderr, "[info] image writers finished %.1f ms after the last shot\n", now_ms() - tw);
   return reports;
 }
 
@@ -237,11 +244,19 @@ void Tracer::save_buffer(const std::string& path_in, int channel_id, int gpu) {
   } else {
     check(m_ctx[gpu], asuna_read_channel(m_ctx[gpu], channel_id, data.data()), "asuna_read_channel");
   }
-  if (m_tis.output_f32) write_npy_f32(path + ".npy", {(size_t)h, (size_t)w, 4}, data.data());
+  // Encoding and writing happen on worker threads while the next shot renders (a 1080p PNG is ~30 ms of deflate even in
+  // bands; four files per shot used to be most of a multi-shot job's wall time).  The pixels are already in host memory
+  // and owned by the task; drain_writers() bounds the number of images in flight and rethrows a writer's exception.
+  auto pixels = std::make_shared<std::vector<float>>(std::move(data));
+  const bool f32 = m_tis.output_f32;
   if (!m_tis.output_scanline || channel_id == 0 || channel_id == -1) {
     // (the reference also takes the scanline branch for channel -1, where its valid-pixel list is stale or empty;
     //  the tone-mapped image is written normally here)
-    write_image(path, w, h, data.data());
+    m_writers.push_back(std::async(std::launch::async, [=] {
+      if (f32) write_npy_f32(path + ".npy", {(size_t)h, (size_t)w, 4}, pixels->data());
+      write_image(path, w, h, pixels->data());
+    }));
+    drain_writers(8);
     return;
   }
   // --output_scanline: channels >= 1 are stored as an (n_valid, 3) float32 NPY under the image's name; the valid
@@ -249,16 +264,29 @@ void Tracer::save_buffer(const std::string& path_in, int channel_id, int gpu) {
   if (channel_id == 1) {
     m_valid_pixel_index.clear();
     for (int idx = 0; idx < w * h; idx++)
-      if (data[4 * (size_t)idx + 2] == 1.0f) {
+      if ((*pixels)[4 * (size_t)idx + 2] == 1.0f) {
         m_valid_pixel_index.push_back(idx);
-        data[4 * (size_t)idx + 2] = (float)idx;
+        (*pixels)[4 * (size_t)idx + 2] = (float)idx;
       }
   }
-  std::vector<float> valid;
-  valid.reserve(m_valid_pixel_index.size() * 3);
+  auto valid = std::make_shared<std::vector<float>>();
+  valid->reserve(m_valid_pixel_index.size() * 3);
   for (int idx : m_valid_pixel_index)
-    for (int c = 0; c < 3; c++) valid.push_back(data[4 * (size_t)idx + c]);
-  write_npy_f32(path, {m_valid_pixel_index.size(), 3}, valid.data());
+    for (int c = 0; c < 3; c++) valid->push_back((*pixels)[4 * (size_t)idx + c]);
+  const size_t n_valid = m_valid_pixel_index.size();
+  m_writers.push_back(std::async(std::launch::async, [=] {
+    if (f32) write_npy_f32(path + ".npy", {(size_t)h, (size_t)w, 4}, pixels->data());
+    write_npy_f32(path, {n_valid, 3}, valid->data());
+  }));
+  drain_writers(8);
+}
+
+// Waits until at most `keep` image writers are still running (0 = all of them), oldest first.
+void Tracer::drain_writers(size_t keep) {
+  while (m_writers.size() > keep) {
+    m_writers.front().get();
+    m_writers.pop_front();
+  }
 }
 
 }  // namespace asuna_host

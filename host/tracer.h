@@ -3,6 +3,8 @@
 // frames of a shot are split f % N == rank (scene replicated) and the (sum w L, sum w) planes are combined with one
 // NCCL reduce to GPU 0 per shot.
 #pragma once
+#include <deque>
+#include <future>
 #include <string>
 #include <vector>
 
@@ -47,6 +49,8 @@ class Tracer {
   std::vector<void*> m_comms;  // ncclComm_t per GPU when n_gpus > 1
   float m_build_ms = 0.f;
   std::vector<int> m_valid_pixel_index;  // --output_scanline state (tracer.cpp:344-345)
+  std::deque<std::future<void>> m_writers;  // image files being encoded / written while the next shot renders
+  void drain_writers(size_t keep);
 };
 
 }  // namespace asuna_host
