@@ -341,7 +341,8 @@ k_shade(const __grid_constant__ SceneView sc, const __grid_constant__ FrameParam
   // The loop is a chain of dependent gathers per path (queue -> slot -> state + hit -> instance -> indices -> vertices ->
   // material), ~70 paths per thread one after the other.  The first hop of the NEXT path (its slot index) is fetched
   // before the current one is shaded.  Measured: fetching the next path's state and hit record ahead as well costs 20
-  // live registers through the whole shader and is 2.7 % (C2) to 5 % (C1) slower than no prefetch at all.
+  // live registers through the whole shader and is 2.7 % (C2) to 5 % (C1) slower than no prefetch at all; a
+  // `prefetch.global.L2` of those lines instead (no registers) is 1-3 % slower too.
   constexpr bool kRadiance = !(KIND == kKindMaterial0 + ASUNA_MAT_DIELECTRIC || KIND == kKindMaterial0 + ASUNA_MAT_CONDUCTOR ||
                                KIND == kKindMaterial0 + ASUNA_MAT_MIRROR);  // the delta shaders neither read nor change the
                                                                               // path radiance: 32 B less per hit
