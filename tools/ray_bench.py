@@ -1,6 +1,6 @@
 """C4' ray-throughput check: ~1.3 M-triangle mesh, lambertian, white environment, 1080p.
 Incoherent rays = closest-hit rays at depth >= 2 (after a cosine-hemisphere bounce).
-usage: python tools/ray_bench.py [subdiv=8] [frames=16] [scene=rays|glass|field|pbr]"""
+usage: python tools/ray_bench.py [subdiv=8] [frames=16] [scene=rays|glass|field|pbr|cornell]"""
 import json
 import os
 import sys
@@ -23,6 +23,8 @@ elif which == "rays_merged":  # same geometry as one mesh / one instance: what a
     sc.instances = sc.instances[:1]
 elif which == "pbr":  # C3: textured PBR spheres, sun/sky + point light
     sc = scenes.pbr_spheres(1920, 1080, depth=5, subdiv=subdiv)
+elif which == "cornell":  # C1: 36 triangles, 512 x 512, depth 5
+    sc = scenes.cornell(512, 512, spp=64, depth=5)
 elif which == "glass":
     sc = scenes.glass_blob(1920, 1080, subdiv=subdiv, env_size=(2048, 1024))
 else:
