@@ -112,7 +112,7 @@ k_trace_closest(const __grid_constant__ SceneView sc, PathState ps, Counters* cn
 }
 
 template <bool SINGLE>
-__global__ void __launch_bounds__(kTraceThreads, SINGLE ? ASUNA_TRACE_MIN_BLOCKS_SINGLE : ASUNA_TRACE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kTraceThreads, SINGLE ? ASUNA_SHADOW_MIN_BLOCKS_SINGLE : ASUNA_TRACE_MIN_BLOCKS)
 k_trace_shadow(const __grid_constant__ SceneView sc, PathState ps, Counters* cnt, int iter) {
   ShadowPolicy pol{ps};  // (prepared-ray staging measured -3 % on the short any-hit traversals: not used here)
   trace_persistent<true, false, SINGLE, false>(sc, pol, cnt->shadow[iter], &cnt->ticket_shadow[iter], &cnt->stack_overflow,
@@ -672,7 +672,7 @@ int launch_shade(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, cons
 }
 void launch_trace_shadow(cudaStream_t s, const LaunchDims& ld, const SceneView& sc, const PathState& ps, Counters* cnt,
                          int iter) {
-  if (sc.single_root != 0xFFFFFFFFu) k_trace_shadow<true><<<ld.trace_blocks_single, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
+  if (sc.single_root != 0xFFFFFFFFu) k_trace_shadow<true><<<ld.shadow_blocks_single, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
   else k_trace_shadow<false><<<ld.trace_blocks, kTraceThreads, 0, s>>>(sc, ps, cnt, iter);
 }
 void launch_accumulate(cudaStream_t s, const FrameParams& fp, const PathState& ps, const OutputImages& out) {
@@ -730,6 +730,9 @@ cudaError_t query_launch_dims(LaunchDims& ld, int sm_count) {
   e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest<false, true>, kTraceThreads, 0);
   if (e != cudaSuccess) return e;
   ld.trace_blocks_single = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_shadow<true>, kTraceThreads, 0);
+  if (e != cudaSuccess) return e;
+  ld.shadow_blocks_single = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
   return shade_occupancy(ld, sm_count, std::make_integer_sequence<uint32_t, kNumKinds>{});
 }
 

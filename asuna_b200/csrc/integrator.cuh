@@ -11,6 +11,7 @@ struct OutputImages {
 struct LaunchDims {
   uint32_t trace_blocks = 0;  // persistent grids: SM count x resident blocks per SM
   uint32_t trace_blocks_single = 0;  // same for the single-level kernels (fewer registers, one more block per SM)
+  uint32_t shadow_blocks_single = 0;  // ... and for the single-level any-hit kernel (one more again)
   uint32_t shade_blocks[kNumKinds] = {};  // per hit kind (register use differs per material)
 };
 
