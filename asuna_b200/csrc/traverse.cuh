@@ -22,7 +22,10 @@
 
 namespace asuna {
 
-constexpr int kTraceThreads = 128;
+#ifndef ASUNA_TRACE_THREADS
+#define ASUNA_TRACE_THREADS 128
+#endif
+constexpr int kTraceThreads = ASUNA_TRACE_THREADS;
 #ifndef ASUNA_TRACE_MIN_BLOCKS
 #define ASUNA_TRACE_MIN_BLOCKS 6  // two-level kernels, 80 registers: 24 resident warps per SM (measured best; 7 spills)
 #endif
