@@ -724,6 +724,17 @@ static cudaError_t shade_occupancy(LaunchDims& ld, int sm_count, std::integer_se
 
 cudaError_t query_launch_dims(LaunchDims& ld, int sm_count) {
   int per_sm = 0;
+  {
+    // The single-level closest-hit kernel keeps 11 KB of prepared rays per block in shared memory, 79 KB per SM at 7
+    // blocks.  Left alone the driver configures 132 KB of shared memory for it (ncu launch__shared_mem_config_size), which
+    // takes 32 KB of L1 away from the node fetches; asking for the next smaller configuration (100 KB) gives them back.
+    int carveout = 40;  // per cent of the 228 KB maximum
+    if (const char* t = getenv("ASUNA_TRACE_CARVEOUT")) carveout = atoi(t);
+    if (carveout >= 0) {
+      cudaFuncSetAttribute(k_trace_closest<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+      cudaFuncSetAttribute(k_trace_closest<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout, carveout);
+    }
+  }
   cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_trace_closest<false, false>, kTraceThreads, 0);
   if (e != cudaSuccess) return e;
   ld.trace_blocks = (uint32_t)(sm_count * (per_sm > 0 ? per_sm : 1));
