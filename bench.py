@@ -382,32 +382,40 @@ def main():
         if sc.envmap is not None:
             sc.envmap = tuple(pin(np.ascontiguousarray(a, np.float32)) for a in sc.envmap)
         sc.meshes = [(pin(v), pin(i)) for v, i in sc.meshes]
-        barrier()
-        t0 = time.perf_counter()
-        ctx = capi.Context(gpu_id=local)
-        t1 = time.perf_counter()
-        tti_build_ms = sc.upload(ctx)
-        ctx.set_partition(rank, world)
-        t2 = time.perf_counter()
-        sc.begin_shot(ctx, 0)
-        ctx.render_frames(args.tti_spp)  # asynchronous: the launches are queued, the host goes on
-        img = ctx.pinned_image() if rank == 0 else None  # page-locked read-back buffer, allocated while the GPU renders
-        ctx.sync()
-        t3 = time.perf_counter()
-        resolve()
-        if rank == 0:
-            ctx.read_channel(0, out=img)
-        t4 = time.perf_counter()
-        barrier()
-        t5 = time.perf_counter()
-        tt = torch.tensor([t5 - t0, t1 - t0, t2 - t1, t3 - t2, t4 - t3], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        tt = tt.tolist()
+        # the whole job three times, the median reported (every run listed): a run right after a 3 GB context was torn down
+        # occasionally pays tens of milliseconds inside the driver (context creation, the first copies) that a fresh
+        # process does not
+        runs = []
+        for rep in range(3):
+            if rep:
+                ctx.close()
+            barrier()
+            t0 = time.perf_counter()
+            ctx = capi.Context(gpu_id=local)
+            t1 = time.perf_counter()
+            tti_build_ms = sc.upload(ctx)
+            ctx.set_partition(rank, world)
+            t2 = time.perf_counter()
+            sc.begin_shot(ctx, 0)
+            ctx.render_frames(args.tti_spp)  # asynchronous: the launches are queued, the host goes on
+            img = ctx.pinned_image() if rank == 0 else None  # page-locked read-back buffer, allocated while the GPU renders
+            ctx.sync()
+            t3 = time.perf_counter()
+            resolve()
+            if rank == 0:
+                ctx.read_channel(0, out=img)
+            t4 = time.perf_counter()
+            barrier()
+            t5 = time.perf_counter()
+            tt = torch.tensor([t5 - t0, t1 - t0, t2 - t1, t3 - t2, t4 - t3], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            runs.append((tt.tolist(), tti_build_ms))
+        tt, tti_build_ms = sorted(runs, key=lambda r: r[0][0])[1]
         tti = {"value": tt[0], "unit": "s", "spp": args.tti_spp, "scaling": "strong",
                "create_context_s": tt[1], "upload_and_build_s": tt[2], "bvh_build_ms": tti_build_ms, "render_s": tt[3],
                "reduce_resolve_readback_s": tt[4],
-               "samples_per_s": args.tti_spp * n_px / tt[0]}
+               "samples_per_s": args.tti_spp * n_px / tt[0], "runs_s": [r[0][0] for r in runs], "reported": "median of 3"}
 
     # ---- the north star's other figures, rank 0 only: C4' (1.31 M triangles) incoherent rays/s, BVH build at 1.31 M and
     # 32.8 M triangles
